@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Benchmark of the PINN training hot path: residual+gradient collocation points/sec.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference ...                      (CPU baseline arm, same metric/config)
+
+A step = one full loss + flat-weight-gradient evaluation (jet forward, PDE residual, data misfit,
+reverse sweep, cross-GPU reduction of [grad | sums], loss finalisation) over the whole synthetic
+collocation set of BASELINE.json configs[4]: 16,777,216 points, [4]+[256]x8+[4] tanh MLP,
+Navier_Stokes residual on (t,x,y) with z not differentiated, MSE on the 4 outputs.  The point set
+is fixed (strong scaling): with N GPUs every rank owns a contiguous 1/N shard.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[4] / SURVEY.md 8(d) primary
+    "synthetic16M_256x8_nswe": dict(
+        layers=[4] + [256] * 8 + [4], kind="Navier_Stokes", dirs={"t": 0, "x": 1, "y": 2},
+        fields={"h": 0, "z": 1, "u": 2, "v": 3}, target_cols=[0, 1, 2, 3], n=16 * (1 << 20)),
+    # SURVEY.md 8(d) secondary (train_newmethod form)
+    "synthetic16M_256x8_cont": dict(
+        layers=[2] + [256] * 8 + [3], kind="continuity_only", dirs={"x": 0, "y": 1},
+        fields={"U": 0, "V": 1, "h": 2}, target_cols=[0, 1], n=16 * (1 << 20)),
+}
+CHUNK = 1 << 21   # points per deterministic generation chunk (seed = 1234 + chunk index)
+
+
+def flops_per_point(w):
+    """F = 6 (1+k) sum_l in_l*out_l (jet forward 2(1+k)S, reverse 4(1+k)S)."""
+    L = w["layers"]
+    return 6 * (1 + len(w["dirs"])) * sum(L[i] * L[i + 1] for i in range(len(L) - 1))
+
+
+def make_shard(w, lo, hi, pin):
+    """Synthetic points [lo,hi): inputs U(-1,1), targets N(0,0.05^2); independent of world size."""
+    d, nt = w["layers"][0], len(w["target_cols"])
+    X = torch.empty(hi - lo, d, dtype=torch.float32, pin_memory=pin)
+    T = torch.empty(hi - lo, nt, dtype=torch.float32, pin_memory=pin)
+    c0, c1 = lo // CHUNK, (hi + CHUNK - 1) // CHUNK
+    for c in range(c0, c1):
+        g = torch.Generator().manual_seed(1234 + c)
+        xs = torch.rand(CHUNK, d, generator=g) * 2 - 1
+        ts = 0.05 * torch.randn(CHUNK, nt, generator=g)
+        a, b = max(lo, c * CHUNK), min(hi, (c + 1) * CHUNK)
+        X[a - lo:b - lo] = xs[a - c * CHUNK:b - c * CHUNK]
+        T[a - lo:b - lo] = ts[a - c * CHUNK:b - c * CHUNK]
+    return X, T
+
+
+def init_params(w):
+    """weights of DNN(layers, 0.0, 'xavier') under torch.manual_seed(1234)."""
+    from pinn_depthestimation_b200.dnn import DNN
+    torch.manual_seed(1234)
+    m = DNN(w["layers"], 0.0, "xavier")
+    return m.flat_params().clone()
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names)
+                   if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": reasons}
+
+
+def cpu_port_throughput(w, n_sample, steps, warmup, threads):
+    """The reference's CPU algorithm (torch autograd with create_graph, oracle/autograd_port.py)
+    on a bounded sample of the same workload; returns (points/s, seconds per step)."""
+    from oracle import autograd_port as ap
+    from oracle import jet_oracle as jo
+    torch.set_num_threads(threads)
+    spec = dict(layers=w["layers"], activation="tanh", kind=w["kind"], dirs=w["dirs"],
+                fields=w["fields"], target_cols=w["target_cols"])
+    assert spec["kind"] in (jo.NSWE, jo.CONT_ONLY)
+    X, T = make_shard(w, 0, n_sample, pin=False)
+    flat = init_params(w)
+    for _ in range(warmup):
+        ap.loss_and_grad(spec, flat, X, T)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ap.loss_and_grad(spec, flat, X, T)
+    dt = (time.perf_counter() - t0) / steps
+    return n_sample / dt, dt
+
+
+def run_reference(args, w, name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_sample = args.cpu_points
+    v, dt = cpu_port_throughput(w, n_sample, args.steps, args.warmup, threads)
+    line = {
+        "impl": "reference", "metric": "residual+grad collocation points/sec", "value": v,
+        "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "layers": w["layers"], "residual": w["kind"],
+                   "n_points": w["n"], "sample_points_per_step": n_sample},
+        "cpu_baseline": {"value": v, "unit": "points/s", "cores": threads, "kind": "port",
+                         "sample": f"{n_sample} of {w['n']} points per step; torch-autograd "
+                                   "restatement of dnn.py+physics.py+loss.backward() "
+                                   "(oracle/autograd_port.py); /root/reference cannot travel"},
+        "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="synthetic16M_256x8_nswe", choices=list(WORKLOADS))
+    ap.add_argument("--points", type=int, default=0, help="override total point count (dev only)")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--cpu-points", type=int, default=16384)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    name = args.workload
+    w = dict(WORKLOADS[name])
+    if args.points:
+        w["n"] = args.points
+    if args.impl == "reference":
+        return run_reference(args, w, name)
+
+    import torch.distributed as dist
+    from pinn_depthestimation_b200 import PassSpec, _cabi
+    from pinn_depthestimation_b200.fused import JetLoss
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    _cabi.lib()   # fail loudly if the extension is not built
+
+    n_total = w["n"]
+    lo, hi = rank * n_total // world, (rank + 1) * n_total // world
+    Xh, Th = make_shard(w, lo, hi, pin=True)
+    X, T = Xh.to(dev), Th.to(dev)
+    params_h = init_params(w).pin_memory()
+    params = params_h.to(dev)
+    grad = torch.empty_like(params)
+    spec = PassSpec(layers=w["layers"], kind=w["kind"], dirs=w["dirs"], fields=w["fields"],
+                    target_cols=w["target_cols"], precision=args.precision)
+    jl = JetLoss(spec, X, T, group=group)
+    P = params.numel()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    # ---- value: inputs resident in HBM -------------------------------------------------------
+    for _ in range(args.warmup):
+        jl.loss_and_grad(params, grad)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    k0, k1 = [ev() for _ in range(args.steps)], [ev() for _ in range(args.steps)]
+    e0, e1 = ev(), ev()
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        # the jet kernel alone (+ its 2 memsets and the weight-pack kernel, < 0.01 % of it)
+        k0[i].record()
+        jl._launch(params, grad, True)
+        k1[i].record()
+        if world > 1:
+            jl._allreduce(grad)
+        jl._finalize()
+    e1.record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    step_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    kern_ms = max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in zip(k0, k1)])))
+    parts = jl.parts.cpu().numpy()
+    value = n_total / (step_ms * 1e-3)
+
+    # ---- e2e: host buffers in, loss + gradient out, copies inside the timed region -----------
+    grad_h = torch.empty(P, dtype=torch.float32).pin_memory()
+    parts_h = torch.empty(4, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        params.copy_(params_h, non_blocking=True)
+        X.copy_(Xh, non_blocking=True)
+        T.copy_(Th, non_blocking=True)
+        p = jl.loss_and_grad(params, grad)
+        grad_h.copy_(grad, non_blocking=True)
+        parts_h.copy_(p, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller reads loss/grad every step
+
+    e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    h2d = (Xh.numel() + Th.numel() + P) * 4
+    d2h = (P + 4) * 4
+
+    # ---- roofline denominators -----------------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+    F = flops_per_point(w)
+    achieved = F * (hi - lo) / (kern_ms * 1e-3) / 1e12
+    if args.precision == "fp32":
+        # FP32-FMA peak is not in MEASURED_PEAKS.json: measure it here with the library's probe
+        out = torch.zeros(4, device=dev)
+        import ctypes as C
+        fl = C.c_double(0)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        lib = _cabi.lib()
+        best = 0.0
+        for _ in range(3):
+            e0.record()
+            _cabi.check(lib.pinn_fma_probe(_cabi.ptr(out), 4096, 148 * 16, C.byref(fl), st))
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, fl.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        peak, bound, peak_src = best, "fp32_fma", "measured in this run (pinn_fma_probe, FFMA-bound kernel)"
+    else:
+        bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak, bound = bf16 / 2.0, "tensor"
+        peak_src = ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32 runs at half the bf16 rate)"
+                    if peaks else "fallback 1.4 PFLOP/s bf16 sustained / 2")
+    roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel": "pinn::jet_kernel", "kernel_ms": kern_ms,
+                "flops_per_point": F, "points_per_launch": hi - lo,
+                "hbm_gbs_streaming": (hi - lo) * (w["layers"][0] + len(w["target_cols"])) * 4
+                / (kern_ms * 1e-3) / 1e9}
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "residual+grad collocation points/sec", "value": value, "unit": "points/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3"}[args.precision],
+            "data": "synthetic",
+            "config": {"workload": name, "layers": w["layers"], "residual": w["kind"],
+                       "n_points": n_total, "points_per_gpu": hi - lo, "parallelism": f"dp{world}",
+                       "l2_policy": "inputs (%.0f MB per GPU) larger than L2, not flushed"
+                                    % ((Xh.numel() + Th.numel()) * 4 / 1e6)},
+            "loss_parts": [float(v) for v in parts[:3]],
+            "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": "points/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": 3 * args.steps,
+            "gpu_launches_note": "per step: pack_kernel, jet_kernel, finalize_kernel (+2 memsets, "
+                                 "+1 NCCL all-reduce when n_gpus>1)",
+            "roofline": roofline, "clocks": clk,
+        }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, dt = cpu_port_throughput(w, args.cpu_points, 3, 1, threads)
+        line["cpu_baseline"] = {
+            "value": v, "unit": "points/s", "cores": threads, "kind": "port",
+            "sample": f"{args.cpu_points} of {n_total} points, 3 timed evaluations after 1 warm-up, "
+                      f"{dt:.2f} s each; torch-autograd restatement of the reference path"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

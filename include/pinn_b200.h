@@ -191,6 +191,10 @@ int pinn_adam_step(float* params, const float* grad, float* exp_avg, float* exp_
                    int64_t n, float lr_host, float beta1, float beta2, float eps,
                    float weight_decay, int64_t step_count, void* stream);
 
+/* Measurement helper (bench.py): launches an FP32-FMA-bound kernel of `ctas` x 256 threads and
+ * reports the FLOPs it executes in *flops_out (host); time it with events on `stream`. */
+int pinn_fma_probe(float* out, int32_t iters, int32_t ctas, double* flops_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -109,15 +109,14 @@ class JetLoss:
         self.n_fid_global = self.fid.n if self.fid is not None else self.res.n
         if group is not None:
             import torch.distributed as dist
+            from . import dist as pdist
             self.world = dist.get_world_size(group)
-            cnt = torch.tensor([self.res.n, self.fid.n if self.fid is not None else self.res.n],
-                               dtype=torch.int64, device=self.device)
-            dist.all_reduce(cnt, group=group)
-            self.n_res_global, self.n_fid_global = int(cnt[0]), int(cnt[1])
+            self.n_res_global, self.n_fid_global = pdist.global_counts(
+                self.res.n, self.fid.n if self.fid is not None else self.res.n, self.device, group)
             if self.res.mask_count is not None:
                 dist.all_reduce(self.res.mask_count, group=group)
             # one fp32 buffer [P + 2*NSUMS] per evaluation
-            self._coll = torch.zeros(self.n_params + 2 * _cabi.NSUMS, dtype=torch.float32,
+            self._coll = torch.zeros(pdist.collective_numel(self.n_params), dtype=torch.float32,
                                      device=self.device)
 
     # ------------------------------------------------------------------
@@ -162,20 +161,9 @@ class JetLoss:
                     _cabi.ptr(self.parts), st), "pinn_loss_finalize")
 
     def _allreduce(self, grad):
-        import torch.distributed as dist
-        P, S = self.n_params, _cabi.NSUMS
-        buf = self._coll
-        if grad is not None:
-            buf[:P].copy_(grad)
-        buf[P:P + S].copy_(self.res.sums)
-        if self.fid is not None:
-            buf[P + S:].copy_(self.fid.sums)
-        dist.all_reduce(buf, group=self.group)
-        if grad is not None:
-            grad.copy_(buf[:P])
-        self.res.sums.copy_(buf[P:P + S])
-        if self.fid is not None:
-            self.fid.sums.copy_(buf[P + S:])
+        from . import dist as pdist
+        pdist.all_reduce_eval(self._coll, grad, self.res.sums,
+                              self.fid.sums if self.fid is not None else None, self.group)
 
     # ------------------------------------------------------------------
     def loss_and_grad(self, params: torch.Tensor, grad: torch.Tensor) -> torch.Tensor:
