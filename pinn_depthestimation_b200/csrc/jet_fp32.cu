@@ -13,13 +13,21 @@
 //   Weights stream through a 3-stage ring of shared-memory chunks filled by 1-D TMA bulk copies
 //   (cp.async.bulk + mbarrier complete_tx) from a packed, zero-padded copy in the workspace.
 #include "common.cuh"
+#include "residual.cuh"
 
 namespace pinn {
 
 constexpr int kStages = 3;
-constexpr float kG = 9.81f;
-constexpr float kCb = (float)(3.0 / 16.0 * 9.81 * 0.78 * 0.78);  // physics.py:77-78
-constexpr float kCd = 0.002f;                                     // physics.py:100
+
+// jets of the network output in the feature-major tile buffer: (col, j) -> buf[col][j*TP + p]
+template <int J, int TP, int MP>
+struct FeatureMajorJets {
+  float* buf;
+  int p;
+  __device__ __forceinline__ float get(int col, int j) const { return buf[col * MP + j * TP + p]; }
+  __device__ __forceinline__ void set(int col, int j, float v) { buf[col * MP + j * TP + p] = v; }
+  __device__ __forceinline__ void add(int col, int j, float v) { buf[col * MP + j * TP + p] += v; }
+};
 
 struct KArgs {
   const float* params;
@@ -287,148 +295,13 @@ __global__ void __launch_bounds__(NT)
       const int p = tid;
       const bool isp = p < TP;
       const long long gp = p0 + p;
-      const bool valid = isp && gp < A.n_points;
+      FeatureMajorJets<J, TP, MP> acc{cur, p};
       float ls[PINN_NSUMS];
-#pragma unroll
-      for (int i = 0; i < PINN_NSUMS; ++i) ls[i] = 0.f;
-#define OV(col, j) cur[(col) * MP + (j) * TP + p]
-#define SEED(col, j, v) cur[(col) * MP + (j) * TP + p] += (v)
-      if (isp) {
-        if (A.out && valid)
-          for (int c = 0; c < o; ++c) A.out[gp * o + c] = OV(c, 0);
-        for (int j = 1; j < J; ++j)
-          if (A.dout[j - 1] && valid)
-            for (int c = 0; c < o; ++c) A.dout[j - 1][gp * o + c] = OV(c, j);
-        // data misfit (train_newmethod.py:129-133 / train.py:136-141)
-        float terr[PINN_MAX_OUT];
-#pragma unroll
-        for (int i = 0; i < PINN_MAX_OUT; ++i) {
-          terr[i] = 0.f;
-          if (A.targets && i < D.n_targets && valid) {
-            terr[i] = OV(D.target_cols[i], 0) - A.targets[gp * D.n_targets + i];
-            ls[PINN_SUM_TARGET0 + i] = terr[i] * terr[i];
-          }
-        }
-        const float vf = valid ? 1.f : 0.f;
-        ls[PINN_SUM_NPOINTS] = vf;
-        const float wr = 2.f * D.w_res * A.inv_n_res * vf;
-        if (kind == PINN_RES_CONT_ONLY || kind == PINN_RES_CONT_FTEMP) {
-          const int ch = D.field_cols[0], cU = D.field_cols[1], cV = D.field_cols[2];
-          const float h = OV(ch, 0), hx = OV(ch, 1), hy = OV(ch, 2);
-          const float U = OV(cU, 0), Ux = OV(cU, 1), V = OV(cV, 0), Vy = OV(cV, 2);
-          const float fc = hx * U + h * Ux + hy * V + h * Vy;  // physics.py:20-23
-          ls[PINN_SUM_FC] = fc * fc * vf;
-          const float r = wr * fc;
-          float sh = r * (Ux + Vy);
-          if (kind == PINN_RES_CONT_ONLY) {  // physics.py:27-28
-            const bool m = valid && xin[p * PINN_MAX_IN + D.mask_col] < D.cond_threshold;
-            const float dev = h - D.cond_value;
-            if (m) {
-              ls[PINN_SUM_COND] = dev * dev;
-              ls[PINN_SUM_MASKCNT] = 1.f;
-              sh += 2.f * D.w_res * dev * inv_cnt;
-            }
-          }
-          for (int c = 0; c < NPo; ++c)
-            for (int j = 0; j < J; ++j) OV(c, j) = 0.f;
-          SEED(cU, 0, r * hx);
-          SEED(cV, 0, r * hy);
-          SEED(ch, 0, sh);
-          SEED(cU, 1, r * h);
-          SEED(cV, 2, r * h);
-          SEED(ch, 1, r * U);
-          SEED(ch, 2, r * V);
-        } else if (kind == PINN_RES_NSWE) {
-          if constexpr (J >= 4) {
-            const int ch = D.field_cols[0], cz = D.field_cols[1], cu = D.field_cols[2],
-                      cv = D.field_cols[3];
-            const float h = OV(ch, 0), hx = OV(ch, 2), hy = OV(ch, 3);
-            const float z = OV(cz, 0), zt = OV(cz, 1), zx = OV(cz, 2), zy = OV(cz, 3);
-            const float u = OV(cu, 0), ut = OV(cu, 1), ux = OV(cu, 2), uy = OV(cu, 3);
-            const float v = OV(cv, 0), vt = OV(cv, 1), vx = OV(cv, 2), vy = OV(cv, 3);
-            const float H = h + z, Hx = hx + zx, Hy = hy + zy;
-            const float fc = zt + Hx * u + H * ux + Hy * v + H * vy;      // physics.py:81
-            const float fx = ut + u * ux + v * uy + kG * zx + kCb * Hx * H;  // physics.py:82
-            const float fy = vt + u * vx + v * vy + kG * zy + kCb * Hy * H;  // physics.py:83
-            ls[PINN_SUM_FC] = fc * fc * vf;
-            ls[PINN_SUM_FX] = fx * fx * vf;
-            ls[PINN_SUM_FY] = fy * fy * vf;
-            const float rc = wr * fc, rx = wr * fx, ry = wr * fy;
-            for (int c = 0; c < NPo; ++c)
-              for (int j = 0; j < J; ++j) OV(c, j) = 0.f;
-            const float shz = rc * (ux + vy) + rx * kCb * Hx + ry * kCb * Hy;
-            SEED(ch, 0, shz);
-            SEED(cz, 0, shz);
-            SEED(cu, 0, rc * Hx + rx * ux + ry * vx);
-            SEED(cv, 0, rc * Hy + rx * uy + ry * vy);
-            SEED(ch, 2, rc * u + rx * kCb * H);
-            SEED(ch, 3, rc * v + ry * kCb * H);
-            SEED(cz, 1, rc);
-            SEED(cz, 2, rc * u + rx * (kG + kCb * H));
-            SEED(cz, 3, rc * v + ry * (kG + kCb * H));
-            SEED(cu, 1, rx);
-            SEED(cu, 2, rc * H + rx * u);
-            SEED(cu, 3, rx * v);
-            SEED(cv, 1, ry);
-            SEED(cv, 2, ry * u);
-            SEED(cv, 3, rc * H + ry * v);
-          }
-        } else if (kind == PINN_RES_WAVE_AVG) {
-          if constexpr (J >= 3) {
-            const int ch = D.field_cols[0], cU = D.field_cols[1], cV = D.field_cols[2],
-                      ce = D.field_cols[3], cH = D.field_cols[4], ck = D.field_cols[5];
-            const float h = OV(ch, 0), U = OV(cU, 0), V = OV(cV, 0), eta = OV(ce, 0);
-            const float Hr = OV(cH, 0), kk = OV(ck, 0);
-            const float Ux = OV(cU, 1), Uy = OV(cU, 2), Vx = OV(cV, 1), Vy = OV(cV, 2);
-            const float ex = OV(ce, 1), ey = OV(ce, 2);
-            const float Dp = eta + h;
-            // physics.py:106: E = 1/8**rho*g*Hrms**2 is exactly 0*Hrms^2; the radiation-stress terms
-            // only propagate NaN where sinh(2kh) is 0 or overflows.
-            const float kh2 = 2.f * kk * h, sh_ = sinhf(kh2);
-            const float poison =
-                (0.f * Hr * Hr) * (kh2 / sh_ + 0.5f) + 0.f * (coshf(kh2) / (sh_ * sh_));
-            const float Fx = kCd * U * fabsf(U) / Dp, Fy = kCd * V * fabsf(V) / Dp;
-            const float fc = Ux + Vy;
-            const float fx = U * Ux + V * Uy + kG * ex + Fx + poison;
-            const float fy = U * Vx + V * Vy + kG * ey + Fy + poison;
-            ls[PINN_SUM_FC] = fc * fc * vf;
-            ls[PINN_SUM_FX] = fx * fx * vf;
-            ls[PINN_SUM_FY] = fy * fy * vf;
-            const float rc = wr * fc, rx = wr * fx, ry = wr * fy;
-            for (int c = 0; c < NPo; ++c)
-              for (int j = 0; j < J; ++j) OV(c, j) = 0.f;
-            const float sD = -(rx * Fx + ry * Fy) / Dp;
-            SEED(ch, 0, sD);
-            SEED(ce, 0, sD);
-            SEED(cU, 0, rx * (Ux + 2.f * kCd * fabsf(U) / Dp) + ry * Vx);
-            SEED(cV, 0, rx * Uy + ry * (Vy + 2.f * kCd * fabsf(V) / Dp));
-            SEED(cU, 1, rc + rx * U);
-            SEED(cU, 2, rx * V);
-            SEED(cV, 1, ry * U);
-            SEED(cV, 2, rc + ry * V);
-            SEED(ce, 1, rx * kG);
-            SEED(ce, 2, ry * kG);
-          }
-        } else if (kind == PINN_RES_EXTERNAL) {
-          for (int c = 0; c < NPo; ++c) {
-            OV(c, 0) = (A.seed_out && valid && c < o) ? A.seed_out[gp * o + c] : 0.f;
-            for (int j = 1; j < J; ++j)
-              OV(c, j) = (A.seed_dout[j - 1] && valid && c < o) ? A.seed_dout[j - 1][gp * o + c]
-                                                              : 0.f;
-          }
-        } else {  // PINN_RES_NONE
-          for (int c = 0; c < NPo; ++c)
-            for (int j = 0; j < J; ++j) OV(c, j) = 0.f;
-        }
-        if (A.targets && valid) {
-          const float wf = 2.f * D.w_fid * A.inv_n_fid;
-#pragma unroll
-          for (int i = 0; i < PINN_MAX_OUT; ++i)
-            if (i < D.n_targets) SEED(D.target_cols[i], 0, wf * D.target_w[i] * terr[i]);
-        }
-      }
-#undef OV
-#undef SEED
+      residual_epilogue<J>(D, acc, isp, isp && gp < A.n_points, gp, xin + (isp ? p : 0) * PINN_MAX_IN,
+                           EpiArgs{A.targets, A.seed_out, {A.seed_dout[0], A.seed_dout[1], A.seed_dout[2]},
+                                   A.out, {A.dout[0], A.dout[1], A.dout[2]}, A.inv_n_res, A.inv_n_fid,
+                                   inv_cnt},
+                           ls);
 #pragma unroll
       for (int i = 0; i < PINN_NSUMS; ++i) {
         const float v = warp_sum(ls[i]);
@@ -624,6 +497,29 @@ __global__ void finalize_kernel(const __grid_constant__ pinn_desc_t D, const dou
 }
 
 // --------------------------------------------------------------------------- host side
+// jet_tc.cu
+bool tc_supported(const pinn_desc_t* D, const char** why);
+int tc_workspace(const pinn_desc_t* D, long long n_points, int sms, size_t* packed_bytes, size_t* slab_bytes,
+                 long long* slab_stride, int* grid);
+int run_tc_pass(const pinn_desc_t* D, const pinn_eval_args_t* a, bool bwd, void* workspace, size_t ws_bytes,
+                cudaStream_t st);
+
+static bool is_residual_kind(int k) { return k >= PINN_RES_CONT_ONLY && k <= PINN_RES_WAVE_AVG; }
+
+// Which kernel runs this pass?  TF32 is only defined for PDE-residual passes of 256-wide tanh nets; value-only
+// (fidelity) and external-seed passes always use the FP32 kernel.  Anything else asked for in TF32 is an error.
+static int uses_tc(const pinn_desc_t* D, bool* tc) {
+  *tc = false;
+  if (D->precision == PINN_PREC_FP32 || !is_residual_kind(D->residual_kind)) return PINN_OK;
+  if (D->precision == PINN_PREC_TF32X3)
+    return set_error("precision tf32x3 is not available in this build"), PINN_E_UNSUPPORTED;
+  const char* why = "";
+  if (!tc_supported(D, &why))
+    return set_error("precision tf32 is not available for this net: %s", why), PINN_E_UNSUPPORTED;
+  *tc = true;
+  return PINN_OK;
+}
+
 struct Config {
   int J, TP, NT;
   int wp, stage_floats;
@@ -773,7 +669,22 @@ static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 int workspace_bytes(const pinn_desc_t* D, long long n_points, size_t* bytes) {
   Config c;
-  int rc = make_config(D, true, &c);
+  int rc = validate_desc(D);
+  if (rc) return rc;
+  bool tc = false;
+  rc = uses_tc(D, &tc);
+  if (rc) return rc;
+  if (tc) {
+    int dev = 0, sms = 0, grid = 1;
+    PINN_CUDA(cudaGetDevice(&dev));
+    PINN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    size_t pk = 0, sl = 0;
+    long long stride = 0;
+    tc_workspace(D, n_points, sms, &pk, &sl, &stride, &grid);
+    *bytes = align256(pk) + align256(sl) + 256;
+    return PINN_OK;
+  }
+  rc = make_config(D, true, &c);
   if (rc) return rc;
   long long tiles = (n_points + c.TP - 1) / c.TP;
   long long grid = tiles < c.max_ctas ? tiles : c.max_ctas;
@@ -798,11 +709,20 @@ int run_pass(const pinn_desc_t* D, const pinn_eval_args_t* a, bool bwd, cudaStre
   if (D->residual_kind == PINN_RES_CONT_ONLY && !a->mask_count)
     return set_error("continuity_only needs mask_count (see pinn_mask_count)"), PINN_E_ARG;
   if (((uintptr_t)a->workspace & 255) != 0) return set_error("workspace must be 256-byte aligned"), PINN_E_ARG;
-  if (D->precision != PINN_PREC_FP32)
-    return set_error("precision %d is not available in this build for this net", D->precision), PINN_E_UNSUPPORTED;
+  bool tc = false;
+  rc = uses_tc(D, &tc);
+  if (rc) return rc;
+  if (((uintptr_t)a->params & 15) != 0) return set_error("params must be 16-byte aligned"), PINN_E_ARG;
 
   long long P = 0;
   for (int i = 0; i < D->n_linear; ++i) P += (long long)D->widths[i] * D->widths[i + 1] + D->widths[i + 1];
+  if (tc) {
+    if (!(a->flags & PINN_FLAG_ACCUMULATE)) {
+      if (bwd) PINN_CUDA(cudaMemsetAsync(a->grad, 0, (size_t)P * 4, st));
+      if (a->sums) PINN_CUDA(cudaMemsetAsync(a->sums, 0, PINN_NSUMS * 8, st));
+    }
+    return run_tc_pass(D, a, bwd, a->workspace, a->workspace_bytes, st);
+  }
   long long tiles = (a->n_points + c.TP - 1) / c.TP;
   long long grid = tiles < c.max_ctas ? tiles : c.max_ctas;
   const size_t need = align256((size_t)c.packed_floats * 4) +

@@ -1,0 +1,103 @@
+"""GPU tests of the tensor-core (tcgen05, TF32 operands / FP32 accumulate) path.
+
+Stated bound for TF32 mode (north_star asks for "a stated looser bound"): relative error <= 3e-3 on
+loss / residual / misfit and <= 5e-3 norm-wise on the weight gradient against the float64 reference;
+observed ~7e-4 and ~1e-3 (operands rounded to 10-bit mantissas, tanh.approx)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import jet_oracle as jo
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+TF32_LOSS_RTOL = 3e-3
+TF32_GRAD_RTOL = 5e-3
+
+
+@pytest.mark.parametrize("name", ["wide_nswe", "wide_cont"])
+def test_tf32_matches_reference_golden_within_stated_bound(name):
+    from tests.gpu_util import run_case
+    case, z = cases.load(name)
+    parts, grad, _, _ = run_case(case, precision="tf32")
+    assert abs(parts[2] - z["loss64"]) <= TF32_LOSS_RTOL * abs(z["loss64"])
+    assert abs(parts[0] - z["fidelity64"]) <= TF32_LOSS_RTOL * abs(z["fidelity64"])
+    assert abs(parts[1] - z["residual64"]) <= TF32_LOSS_RTOL * abs(z["residual64"])
+    assert np.all(np.isfinite(grad))
+    assert cases.golden_grad_check(z, grad) <= TF32_GRAD_RTOL
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 100])
+def test_tf32_ragged_tiles(n):
+    from tests.gpu_util import run_case
+    case, _ = cases.load("wide_nswe")
+    parts, grad, _, _ = run_case(case, precision="tf32", n_override=n)
+    sres, _ = cases.specs(case)
+    flat, X, T, _, _ = cases.data(case, np.float64)
+    r = jo.loss_and_grad(sres, flat, X[:n], T[:n])
+    assert abs(parts[2] - r["loss"]) <= TF32_LOSS_RTOL * abs(r["loss"])
+    assert np.linalg.norm(grad - r["grad"]) <= TF32_GRAD_RTOL * np.linalg.norm(r["grad"])
+
+
+def _big(prec, n, dev, kind="Navier_Stokes"):
+    from pinn_depthestimation_b200 import PassSpec
+    from pinn_depthestimation_b200.fused import JetLoss
+    if kind == "Navier_Stokes":
+        layers = [4] + [256] * 8 + [4]
+        kw = dict(dirs={"t": 0, "x": 1, "y": 2}, fields={"h": 0, "z": 1, "u": 2, "v": 3}, target_cols=[0, 1, 2, 3])
+    else:
+        layers = [2] + [256] * 3 + [3]
+        kw = dict(dirs={"x": 0, "y": 1}, fields={"U": 0, "V": 1, "h": 2}, target_cols=[0, 1])
+    flat = torch.from_numpy(jo.make_params(layers, 1234, "tanh", np.float32)).to(dev)
+    g = torch.Generator(device="cpu").manual_seed(7)
+    X = (torch.rand(n, layers[0], generator=g) * 2 - 1).to(dev)
+    T = (0.05 * torch.randn(n, len(kw["target_cols"]), generator=g)).to(dev)
+    spec = PassSpec(layers=layers, kind=kind, precision=prec, **kw)
+    jl = JetLoss(spec, X, T)
+    grad = torch.empty_like(flat)
+    parts = jl.loss_and_grad(flat, grad).clone()
+    torch.cuda.synchronize()
+    return parts, grad, jl
+
+
+@pytest.mark.parametrize("kind", ["Navier_Stokes", "continuity_only"])
+def test_tf32_many_tiles_per_cta_agrees_with_fp32_kernel(kind):
+    """~27 tiles per persistent CTA: exercises every mbarrier phase wrap; FP32 kernel is the yardstick."""
+    dev = torch.device("cuda:0")
+    n = (1 << 17) + 77
+    p32, g32, _ = _big("fp32", n, dev, kind)
+    ptc, gtc, jl = _big("tf32", n, dev, kind)
+    assert torch.isfinite(gtc).all()
+    assert abs(ptc[2].item() - p32[2].item()) <= TF32_LOSS_RTOL * abs(p32[2].item())
+    assert ((gtc - g32).norm() / g32.norm()).item() <= TF32_GRAD_RTOL
+    assert jl.res.sums[13].item() == n
+    # a second evaluation on the same workspace gives the same loss (no state leaks between launches)
+    g2 = torch.empty_like(gtc)
+    p2 = jl.loss_and_grad(torch.from_numpy(jo.make_params([4] + [256] * 8 + [4] if kind == "Navier_Stokes" else [2] + [256] * 3 + [3], 1234, "tanh", np.float32)).to(dev), g2)
+    assert abs(p2[2].item() - ptc[2].item()) <= 1e-6 * abs(ptc[2].item())
+    assert ((g2 - gtc).norm() / gtc.norm()).item() <= 1e-5
+
+
+def test_tf32_forward_only_loss():
+    from pinn_depthestimation_b200.fused import JetLoss
+    from tests.gpu_util import pass_specs
+    dev = torch.device("cuda:0")
+    case, z = cases.load("wide_nswe")
+    spec, _ = pass_specs(case, "tf32")
+    flat, X, T, _, _ = cases.data(case, np.float32)
+    jl = JetLoss(spec, torch.from_numpy(X).to(dev), torch.from_numpy(T).to(dev))
+    out = torch.empty(X.shape[0], 4, device=dev)
+    parts = jl.loss(torch.from_numpy(flat).to(dev), out=out).cpu().numpy()
+    assert abs(parts[2] - z["loss64"]) <= TF32_LOSS_RTOL * abs(z["loss64"])
+    assert np.abs(out.cpu().numpy()[:16] - z["out64_head"]).max() <= 5e-3 * np.abs(z["out64_head"]).max()
+
+
+def test_tf32_is_refused_for_nets_it_does_not_cover():
+    from pinn_depthestimation_b200 import PassSpec
+    from pinn_depthestimation_b200.fused import JetLoss
+    dev = torch.device("cuda:0")
+    spec = PassSpec(layers=[2] + [20] * 4 + [3], kind="continuity_only", dirs={"x": 0, "y": 1},
+                    fields={"U": 0, "V": 1, "h": 2}, target_cols=[0, 1], precision="tf32")
+    with pytest.raises(RuntimeError, match="tf32"):
+        JetLoss(spec, torch.zeros(8, 2, device=dev), torch.zeros(8, 2, device=dev))
