@@ -179,7 +179,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const int kind = D.residual_kind;
   const int my_tiles = (A.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   float* slab = A.slab + (long long)blockIdx.x * A.slab_stride;
-  float* zt = slab + (size_t)(L - 2) * TC_M * TC_H;   // T-image of the current Zbar
+  float* slab_r = slab + (size_t)(L - 2) * TC_M * TC_H;      // thread-private row images (reverse loads)
+  float* zt = slab_r + (size_t)(L - 2) * TC_M * TC_H;        // T-image of the current Zbar
   const long long P0 = (long long)d * TC_H + TC_H;               // params of layer 0
   const long long PH = (long long)TC_H * TC_H + TC_H;            // params of a hidden->hidden layer
   const long long poffL = P0 + (long long)NHH * PH;              // params offset of the last layer
@@ -342,15 +343,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         *reinterpret_cast<float4*>(op + (f0 / 4 + q) * OP_LBO + m * 16) =
             make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     };
-    // T-image (row-transposed, 16-row chunks): float index of (row m, feature f)
-    const size_t t_row = (size_t)(m >> 4) * TC_STAGE_FLOATS + (size_t)((m & 15) >> 2) * (TC_H * 4) + (m & 3);
-    auto t_store = [&](float* img, int f0, const float (&v)[16]) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) img[t_row + (size_t)(f0 + i) * 4] = v[i];
+    // T-image (row-transposed, 16-row chunks): (row m, feature f) at float (m/16)*4096 + ((m%16)/4)*1024 + f*4 + m%4.
+    // Each warp transposes the 32 rows x 128 features it owns out of the operand image: 4 conflict-free
+    // LDS.32 (the 4 rows of a quad) -> one coalesced 16-byte store per feature.
+    auto t_copy = [&](float* img) {
+      __syncwarp();
+#pragma unroll 4
+      for (int itc = 0; itc < 32; ++itc) {
+        const int idx = itc * 32 + lane;
+        const int q = idx >> 7, f = half * 128 + (idx & 127);
+        const unsigned char* src = op + (f >> 2) * OP_LBO + (sp * 32 + 4 * q) * 16 + (f & 3) * 4;
+        float4 v;
+        v.x = *reinterpret_cast<const float*>(src);
+        v.y = *reinterpret_cast<const float*>(src + 16);
+        v.z = *reinterpret_cast<const float*>(src + 32);
+        v.w = *reinterpret_cast<const float*>(src + 48);
+        *reinterpret_cast<float4*>(img + (size_t)(2 * sp + (q >> 2)) * TC_STAGE_FLOATS + (size_t)(q & 3) * (TC_H * 4) +
+                                   (size_t)f * 4) = v;
+      }
     };
-    auto t_load = [&](const float* img, int f0, float (&v)[16]) {
+    // R-image: thread-private float4 slots [(block b, q)][worker thread] (coalesced), for the reverse loads
+    const int wtid = tid;  // workers are threads 0..255
+    auto r_store = [&](float* img, int b, const float (&v)[16]) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = img[t_row + (size_t)(f0 + i) * 4];
+      for (int q = 0; q < 4; ++q)
+        reinterpret_cast<float4*>(img)[(size_t)(b * 4 + q) * TC_WORKERS + wtid] =
+            make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    };
+    auto r_load = [&](const float* img, int b, float (&v)[16]) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 t = reinterpret_cast<const float4*>(img)[(size_t)(b * 4 + q) * TC_WORKERS + wtid];
+        v[4 * q] = t.x, v[4 * q + 1] = t.y, v[4 * q + 2] = t.z, v[4 * q + 3] = t.w;
+      }
     };
     // forward activation on 16 features: z (pre-activation of this row) -> post-activation jets
     auto activate = [&](float (&z)[16], const float* bias) {
@@ -404,10 +429,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
           activate(z, nullptr);
           store_op(f0, z);
-          if (BWD && NHH >= 1) t_store(slab, f0, z);
+          if (BWD && NHH >= 1) r_store(slab_r, b, z);
         }
       }
       signal_ready();
+      if (BWD && NHH >= 1) t_copy(slab);
       // ---------------- hidden layers 1..L-2 on the tensor cores ----------------
       for (int l = 1; l <= L - 2; ++l) {
         wait_mma();
@@ -435,9 +461,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             }
           }
           store_op(f0, z);
-          if (BWD && l <= L - 3) t_store(slab + (size_t)l * TC_M * TC_H, f0, z);
+          if (BWD && l <= L - 3) r_store(slab_r + (size_t)l * TC_M * TC_H, b, z);
         }
         if (l < L - 2) signal_ready();
+        if (BWD && l <= L - 3) t_copy(slab + (size_t)l * TC_M * TC_H);
       }
       if (BWD) {
         // the TMA engine reads the slab at L2: publish the generic-proxy stores at GPU scope first
@@ -535,9 +562,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
           adjoint(ab, act);
           store_op(f0, ab);
-          t_store(zt, f0, ab);
         }
       }
+      t_copy(zt);
       __threadfence();
       fence_async_proxy();
       mbar_arrive(zt_ready);
@@ -582,12 +609,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           const int f0 = half * 128 + b * 16;
           float ab[16], act[16];
           tmem_ld16(tmem_row + (uint32_t)f0, ab);
-          t_load(slab + (size_t)(l - 1) * TC_M * TC_H, f0, act);
+          r_load(slab_r + (size_t)(l - 1) * TC_M * TC_H, b, act);
           adjoint(ab, act);
           store_op(f0, ab);
-          if (l > 1) t_store(zt, f0, ab);   // Zbar_{l-1}^T feeds the next weight-gradient job
         }
         if (l > 1) {
+          t_copy(zt);                       // Zbar_{l-1}^T feeds the next weight-gradient job
           __threadfence();
           fence_async_proxy();
           mbar_arrive(zt_ready);
@@ -680,7 +707,7 @@ int tc_workspace(const pinn_desc_t* D, long long n_points, int sms, size_t* pack
   if (g < 1) g = 1;
   *grid = (int)g;
   *packed_bytes = (size_t)(L - 2) * 2 * TC_H * TC_H * 4;
-  *slab_stride = (long long)(L - 1) * TC_M * TC_H;   // (L-2) layer outputs + the Zbar spill
+  *slab_stride = (long long)(2 * (L - 2) + 1) * TC_M * TC_H;   // T- and R-images of (L-2) layer outputs + Zbar spill
   *slab_bytes = (size_t)g * (size_t)(*slab_stride) * 4;
   return PINN_OK;
 }
