@@ -43,6 +43,7 @@ constexpr int OP_LBO = TC_M * 16 + 16;     // 2064
 constexpr int OP_BYTES = (TC_H / 4) * OP_LBO;
 constexpr int TC_WCHUNKS = TC_H * TC_H * 4 / TC_STAGE_BYTES;   // 16 chunks per weight image
 constexpr int TC_SCHUNKS = TC_M * TC_H * 4 / TC_STAGE_BYTES;   // 8 chunks per slab entry
+constexpr int TC_MAX_HH = 7;               // hidden->hidden layers whose biases are staged in shared memory
 
 struct TcArgs {
   const float* params;
@@ -108,6 +109,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 16 TMEM lanes x 32 columns; thread T gets, for u = 0..3: v[4u], v[4u+1] = (lane T/4,     cols 8u + 2(T%4) + {0,1})
+//                                                         v[4u+2], v[4u+3] = (lane T/4 + 8, same cols)
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -152,6 +170,14 @@ struct RowMajorJets {  // output jets of one point in the [128 rows][8] area, ro
   __device__ __forceinline__ void add(int col, int j, float v) { outs[(4 * p + j) * 8 + col] += v; }
 };
 
+#ifdef PINN_TC_DEBUG
+#define TCT_DECL long long tct[16] = {0}; long long tct0 = clock64();
+#define TCT(i) { const long long t_ = clock64(); tct[i] += t_ - tct0; tct0 = t_; }
+#else
+#define TCT_DECL
+#define TCT(i)
+#endif
+
 template <bool BWD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     jet_tc_kernel(const __grid_constant__ pinn_desc_t D, const __grid_constant__ TcArgs A) {
@@ -162,7 +188,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   float* wls = w0s + TC_H * 8;                                    // [8][H]  Wlast[c][f]
   float* outs = wls + 8 * TC_H;                                   // [128][8] output jets / seeds
   float* xin = outs + TC_M * 8;                                   // [32][8]
-  double* red = reinterpret_cast<double*>(xin + TC_TP * 8);       // [16]
+  float* bias_s = xin + TC_TP * 8;                                // [TC_MAX_HH][H] hidden-layer biases
+  double* red = reinterpret_cast<double*>(bias_s + TC_MAX_HH * TC_H);  // [16]
   uint64_t* full = reinterpret_cast<uint64_t*>(red + PINN_NSUMS);  // [S]
   uint64_t* empty = full + TC_STAGES;                             // [S]
   uint64_t* op_ready = empty + TC_STAGES;
@@ -205,6 +232,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   for (int i = tid; i < 8 * TC_H; i += TC_THREADS) {
     const int c = i / TC_H, f = i - c * TC_H;
     wls[i] = c < o ? A.params[poffL + (long long)c * TC_H + f] : 0.f;
+  }
+  for (int i = tid; i < TC_MAX_HH * TC_H; i += TC_THREADS) {
+    const int hl = i / TC_H, f = i - hl * TC_H;
+    bias_s[i] = hl < NHH ? A.params[P0 + (long long)hl * PH + (long long)TC_H * TC_H + f] : 0.f;
   }
   if (warp == 9) {
     tmem_alloc(tmem_ptr, 512);
@@ -326,6 +357,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t tmem_row = tmem_base + ((uint32_t)(sp * 32) << 16);
     const float inv_cnt = (kind == PINN_RES_CONT_ONLY && A.mask_count) ? 1.0f / *A.mask_count : 0.f;
     int mj = 0;  // MMA jobs waited for
+    TCT_DECL
     auto wait_mma = [&]() {
       mbar_wait(mma_done, (uint32_t)(mj & 1));
       ++mj;
@@ -362,13 +394,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                                    (size_t)f * 4) = v;
       }
     };
-    // R-image: thread-private float4 slots [(block b, q)][worker thread] (coalesced), for the reverse loads
+    // R-image: thread-private float4 slots [(block b, q)][worker thread] (coalesced), for the reverse loads;
+    // written as a copy of this thread's own row out of the operand image, after the MMA has been released
     const int wtid = tid;  // workers are threads 0..255
-    auto r_store = [&](float* img, int b, const float (&v)[16]) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        reinterpret_cast<float4*>(img)[(size_t)(b * 4 + q) * TC_WORKERS + wtid] =
-            make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    auto r_copy = [&](float* img) {
+#pragma unroll 8
+      for (int c = 0; c < 32; ++c)
+        reinterpret_cast<float4*>(img)[(size_t)c * TC_WORKERS + wtid] =
+            *reinterpret_cast<const float4*>(op + (half * 32 + c) * OP_LBO + m * 16);
     };
     auto r_load = [&](const float* img, int b, float (&v)[16]) {
 #pragma unroll
@@ -409,6 +442,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         xin[i] = (c < d && gp < A.n_points) ? A.inputs[gp * d + c] : 0.f;
       }
       worker_bar();
+      TCT(0)
       // ---------------- layer 0 (d -> 256) on the FP32 pipes ----------------
       {
         const int dircol = (j >= 1 && j - 1 < D.n_dirs) ? D.dir_cols[j - 1] : -1;
@@ -429,42 +463,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
           activate(z, nullptr);
           store_op(f0, z);
-          if (BWD && NHH >= 1) r_store(slab_r, b, z);
         }
       }
+      TCT(1)
       signal_ready();
-      if (BWD && NHH >= 1) t_copy(slab);
+      if (BWD && NHH >= 1) {
+        r_copy(slab_r);
+        t_copy(slab);
+      }
+      TCT(3)
       // ---------------- hidden layers 1..L-2 on the tensor cores ----------------
       for (int l = 1; l <= L - 2; ++l) {
         wait_mma();
-        const float* bias_g = A.params + P0 + (long long)(l - 1) * PH + (long long)TC_H * TC_H;
+        TCT(2)
+        const float* bias_l = (l - 1 < TC_MAX_HH) ? bias_s + (l - 1) * TC_H
+                                                  : A.params + P0 + (long long)(l - 1) * PH + (long long)TC_H * TC_H;
         for (int b = 0; b < 8; ++b) {
           const int f0 = half * 128 + b * 16;
-          float z[16], bias[16];
+          float z[16];
           tmem_ld16(tmem_row + (uint32_t)f0, z);
+          // value rows: a = tanh(z + b); tangent rows: s * zdot with s = 1 - a^2 of the point's value row
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 bv = *reinterpret_cast<const float4*>(bias_g + f0 + 4 * q);
-            bias[4 * q] = bv.x, bias[4 * q + 1] = bv.y, bias[4 * q + 2] = bv.z, bias[4 * q + 3] = bv.w;
-          }
-          if (j != 0) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) bias[i] = 0.f;
-          }
-          // value rows: a = tanh(z + b); tangent rows keep z (their "bias" is 0 and tanh is unused)
-          {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float a = tanh_approx(z[i] + bias[i]);
-              const float al = __shfl_sync(0xffffffffu, a, leader);
-              z[i] = round_tf32(j == 0 ? a : (1.f - al * al) * z[i]);
-            }
+          for (int i = 0; i < 16; ++i) {
+            const float a = tanh_approx(z[i] + bias_l[f0 + i]);
+            const float al = __shfl_sync(0xffffffffu, a, leader);
+            z[i] = round_tf32(j == 0 ? a : (1.f - al * al) * z[i]);
           }
           store_op(f0, z);
-          if (BWD && l <= L - 3) r_store(slab_r + (size_t)l * TC_M * TC_H, b, z);
         }
+        TCT(1)
         if (l < L - 2) signal_ready();
-        if (BWD && l <= L - 3) t_copy(slab + (size_t)l * TC_M * TC_H);
+        if (BWD && l <= L - 3) {
+          r_copy(slab_r + (size_t)l * TC_M * TC_H);
+          t_copy(slab + (size_t)l * TC_M * TC_H);
+        }
+        TCT(3)
       }
       if (BWD) {
         // the TMA engine reads the slab at L2: publish the generic-proxy stores at GPU scope first
@@ -511,6 +544,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
       }
       worker_bar();
+      TCT(4)
       if (!BWD) continue;
 
       // =============================== reverse ===============================
@@ -569,6 +603,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       fence_async_proxy();
       mbar_arrive(zt_ready);
       worker_bar();
+      TCT(5)
       // ---- hidden layers L-2 .. 1 ----
       for (int l = L - 2; l >= 1; --l) {
         const long long poff = P0 + (long long)(l - 1) * PH;
@@ -582,45 +617,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           atomicAdd(A.grad + poff + (long long)TC_H * TC_H + f, s);
         }
         signal_ready();
+        TCT(6)
         // weight gradient: drain D_0 / D_1 (rows = Zbar feature n, columns = A_in feature k)
         wait_mma();
+        TCT(7)
+        // 16x256b loads: the 4 lanes of a quad hold 8 consecutive columns of one row, so every RED
+        // instruction updates full 32-byte sectors (8 rows x 32 B) instead of 32 half-filled ones
         for (int h = 0; h < 2; ++h) {
-          float* grow = A.grad + poff + (long long)(h * 128 + m) * TC_H;
-          for (int b = 0; b < 8; ++b) {
-            const int k0 = half * 128 + b * 16;
-            float v[16];
-            tmem_ld16(tmem_row + (uint32_t)(h * 256 + k0), v);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) red_add_v4(grow + k0 + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-#ifdef PINN_TC_DEBUG
-            {
-              float sa = 0.f;
-              for (int i = 0; i < 16; ++i) sa += fabsf(v[i]);
-              sa = warp_sum_tc(sa);
-              if (lane == 0) atomicAdd(A.sums + 14, (double)sa);
+          for (int g = 0; g < 2; ++g) {
+            const int row = h * 128 + sp * 32 + g * 16 + (lane >> 2);
+            float* grow = A.grad + poff + (long long)row * TC_H + half * 128 + 2 * (lane & 3);
+            const uint32_t ta = tmem_base + ((uint32_t)(sp * 32 + g * 16) << 16) + (uint32_t)(h * 256 + half * 128);
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) {
+              float v[16];
+              tmem_ld_16x256b_x4(ta + (uint32_t)(cb * 32), v);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                red_add_v2(grow + cb * 32 + 8 * u, v[4 * u], v[4 * u + 1]);
+                red_add_v2(grow + 8 * TC_H + cb * 32 + 8 * u, v[4 * u + 2], v[4 * u + 3]);
+              }
             }
-#endif
           }
         }
+        TCT(8)
         signal_ready();
         // adjoint through the activation of layer l-1 -> Zbar_{l-1} in place
-        wait_mma();
-        for (int b = 0; b < 8; ++b) {
-          const int f0 = half * 128 + b * 16;
-          float ab[16], act[16];
-          tmem_ld16(tmem_row + (uint32_t)f0, ab);
-          r_load(slab_r + (size_t)(l - 1) * TC_M * TC_H, b, act);
-          adjoint(ab, act);
-          store_op(f0, ab);
+        {
+          const float* rimg = slab_r + (size_t)(l - 1) * TC_M * TC_H;
+          float act[16], nxt[16];
+          r_load(rimg, 0, act);   // issued before the wait: the loads overlap the adjoint MMA
+          wait_mma();
+          TCT(9)
+          for (int b = 0; b < 8; ++b) {
+            const int f0 = half * 128 + b * 16;
+            float ab[16];
+            if (b < 7) r_load(rimg, b + 1, nxt);
+            tmem_ld16(tmem_row + (uint32_t)f0, ab);
+            adjoint(ab, act);
+            store_op(f0, ab);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) act[i] = nxt[i];
+          }
         }
+        TCT(10)
+        tc_fence_before();
         if (l > 1) {
           t_copy(zt);                       // Zbar_{l-1}^T feeds the next weight-gradient job
           __threadfence();
           fence_async_proxy();
           mbar_arrive(zt_ready);
         }
-        tc_fence_before();
         worker_bar();
+        TCT(11)
       }
       // ---- layer 0: dW0[f][c], db0[f] from Zbar_0 (thread per feature) ----
       {
@@ -648,7 +698,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         atomicAdd(A.grad + (long long)d * TC_H + f, sb);
       }
       worker_bar();
+      TCT(12)
     }
+#ifdef PINN_TC_DEBUG
+    if (blockIdx.x == 0 && tid == 0) {
+      long long tot = 0;
+      for (int i = 0; i < 13; ++i) tot += tct[i];
+      printf("TC phases (cycles per tile, %d tiles): in+bar %lld | L0+fwd-epi %lld | fwd-wait-mma %lld | fwd signal+copies %lld | last+residual %lld | rev-last %lld | db+signal %lld | wait-dW %lld | drain %lld | signal+wait-adj %lld | adj-epi %lld | tcopy+fence+bar %lld | L0-rev %lld | total %lld\n", my_tiles,
+             tct[0] / my_tiles, tct[1] / my_tiles, tct[2] / my_tiles, tct[3] / my_tiles, tct[4] / my_tiles, tct[5] / my_tiles, tct[6] / my_tiles,
+             tct[7] / my_tiles, tct[8] / my_tiles, tct[9] / my_tiles, tct[10] / my_tiles, tct[11] / my_tiles, tct[12] / my_tiles, tot / my_tiles);
+    }
+#endif
   }
 
   // ---------------- teardown ----------------
@@ -682,7 +742,7 @@ __global__ void pack_tc_kernel(const __grid_constant__ pinn_desc_t D, const floa
 // --------------------------------------------------------------------------------------- host side
 constexpr size_t tc_smem_bytes() {
   return (size_t)OP_BYTES + (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)TC_H * 8 * 4 + (size_t)8 * TC_H * 4 +
-         (size_t)TC_M * 8 * 4 + (size_t)TC_TP * 8 * 4 + PINN_NSUMS * 8 + (2 * TC_STAGES + 4) * 8 + 16;
+         (size_t)TC_M * 8 * 4 + (size_t)TC_TP * 8 * 4 + (size_t)TC_MAX_HH * TC_H * 4 + PINN_NSUMS * 8 + (2 * TC_STAGES + 4) * 8 + 16;
 }
 
 // Can this description run on the tensor-core kernel?  (otherwise the caller reports UNSUPPORTED)
