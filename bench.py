@@ -130,6 +130,31 @@ def cpu_port_throughput(w, n_sample, steps, warmup, threads):
     return n_sample / dt, dt
 
 
+def cpu_port_lbfgs(w, n_sample, iters, threads):
+    """torch.optim.LBFGS (ctor as train_newmethod.py:108-117) on the reference algorithm, CPU sample."""
+    from oracle import autograd_port as ap
+    torch.set_num_threads(threads)
+    spec = dict(layers=w["layers"], activation="tanh", kind=w["kind"], dirs=w["dirs"],
+                fields=w["fields"], target_cols=w["target_cols"])
+    X, T = make_shard(w, 0, n_sample, pin=False)
+    p = torch.nn.Parameter(init_params(w))
+    opt = torch.optim.LBFGS([p], lr=1, max_iter=iters, max_eval=iters * 5 // 4 + 1, history_size=100,
+                            tolerance_grad=1e-5, tolerance_change=1e-7, line_search_fn="strong_wolfe")
+
+    def closure():
+        opt.zero_grad()
+        r = ap.loss_and_grad(spec, p.detach(), X, T)
+        p.grad = r["grad"]
+        return r["loss"]
+    t0 = time.perf_counter()
+    opt.step(closure)
+    dt = time.perf_counter() - t0
+    st = opt.state[p]
+    return {"iterations_per_s": st["n_iter"] / dt, "evaluations_per_s": st["func_evals"] / dt,
+            "n_iter": st["n_iter"], "func_evals": st["func_evals"], "ms": dt * 1e3,
+            "n_points": n_sample, "history_size": 100, "line_search_fn": "strong_wolfe"}
+
+
 def run_reference(args, w, name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -137,6 +162,7 @@ def run_reference(args, w, name):
     threads = os.cpu_count() or 1
     n_sample = args.cpu_points
     v, dt = cpu_port_throughput(w, n_sample, args.steps, args.warmup, threads)
+    lb = cpu_port_lbfgs(w, n_sample, args.lbfgs_iters, threads) if args.lbfgs_iters > 0 else None
     line = {
         "impl": "reference", "metric": "residual+grad collocation points/sec", "value": v,
         "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -149,7 +175,7 @@ def run_reference(args, w, name):
                                    "restatement of dnn.py+physics.py+loss.backward() "
                                    "(oracle/autograd_port.py); /root/reference cannot travel"},
         "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "lbfgs": lb,
     }
     print(json.dumps(line), flush=True)
 
@@ -165,6 +191,8 @@ def main():
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"])
     ap.add_argument("--fp32-steps", type=int, default=2, help="timed steps of the FP32 parity-mode side measurement (0 = skip)")
     ap.add_argument("--cpu-points", type=int, default=16384)
+    ap.add_argument("--lbfgs-iters", type=int, default=6,
+                    help="max_iter of the L-BFGS side measurement (BASELINE metric ii); 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     name = args.workload
@@ -270,6 +298,32 @@ def main():
     h2d = (Xh.numel() + Th.numel() + P) * 4
     d2h = (P + 4) * 4
 
+    # ---- second headline metric: L-BFGS iterations/sec (one step(closure) call, train_newmethod.py:204-209) ----
+    lbfgs_side = None
+    if args.lbfgs_iters > 0:
+        from pinn_depthestimation_b200.lbfgs import LBFGS
+        pl = torch.nn.Parameter(params.clone())
+        opt = LBFGS([pl], lr=1, max_iter=args.lbfgs_iters, max_eval=args.lbfgs_iters * 5 // 4 + 1,
+                    history_size=100, tolerance_grad=1e-5, tolerance_change=1e-7,
+                    line_search_fn="strong_wolfe")      # ctor as train_newmethod.py:108-117
+
+        class _Closure:
+            def flat_loss_and_grad(self, fp, fg):
+                return jl.loss_and_grad(fp, fg)
+        barrier()
+        e0.record()
+        opt.step(_Closure())
+        e1.record()
+        barrier()
+        ms_l = max_over_ranks(e0.elapsed_time(e1))
+        st_l = opt.state[pl]
+        lbfgs_side = {"iterations_per_s": st_l["n_iter"] / (ms_l * 1e-3),
+                      "evaluations_per_s": st_l["func_evals"] / (ms_l * 1e-3),
+                      "n_iter": st_l["n_iter"], "func_evals": st_l["func_evals"], "ms": ms_l,
+                      "final_loss": st_l.get("loss"), "history_size": 100,
+                      "line_search_fn": "strong_wolfe", "n_points": n_total}
+        del opt, pl
+
     # ---- side measurement: the FP32 parity mode on the same workload ---------------------------
     fp32_side = None
     if args.precision != "fp32" and args.fp32_steps > 0:
@@ -349,6 +403,7 @@ def main():
                           {"loss_rel": 3e-3, "grad_rel_l2": 5e-3,
                            "mode": "tf32 operands, fp32 accumulate (stated looser bound; tests/test_gpu_tc.py)"}),
             "fp32_parity_mode": fp32_side,
+            "lbfgs": lbfgs_side,
         }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

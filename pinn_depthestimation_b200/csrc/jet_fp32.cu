@@ -99,7 +99,7 @@ struct Cursor {
 template <int J, int TP, int MP>
 __device__ __forceinline__ void gemm_chunk(float (&acc)[J][4][4], const float* __restrict__ xs,
                                            const float* __restrict__ wc, int rowlen, int rows) {
-#pragma unroll 2
+#pragma unroll 4
   for (int k = 0; k < rows; ++k) {
     const float4 w = *reinterpret_cast<const float4*>(wc + k * rowlen);
 #pragma unroll
@@ -341,17 +341,20 @@ __global__ void __launch_bounds__(NT)
             for (int a = 0; a < 4; ++a)
 #pragma unroll
               for (int b = 0; b < 4; ++b) w[a][b] = 0.f;
-            const float* zp = bz + gn * MP;
-            const float* ap = ba + g * MP;
-#pragma unroll 2
+            const float* zr[4];
+            const float* ar[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              zr[a] = bz + (gn + a * NQ) * MP;
+              ar[a] = ba + (g + a * KQ) * MP;
+            }
+#pragma unroll 4
             for (int m = 0; m < M; m += 4) {
               float4 zv[4], av[4];
 #pragma unroll
-              for (int a = 0; a < 4; ++a)
-                zv[a] = *reinterpret_cast<const float4*>(zp + a * NQ * MP + m);
+              for (int a = 0; a < 4; ++a) zv[a] = *reinterpret_cast<const float4*>(zr[a] + m);
 #pragma unroll
-              for (int b = 0; b < 4; ++b)
-                av[b] = *reinterpret_cast<const float4*>(ap + b * KQ * MP + m);
+              for (int b = 0; b < 4; ++b) av[b] = *reinterpret_cast<const float4*>(ar[b] + m);
 #pragma unroll
               for (int a = 0; a < 4; ++a)
 #pragma unroll

@@ -20,6 +20,8 @@ answering d out / d x with forward jets.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import dnn as _dnn
@@ -107,8 +109,10 @@ def _fused(kind, dir_args, field_args):
     if jl is None:
         if len(_CACHE) > 32:
             _CACHE.clear()
+        # PINN_B200_PRECISION=tf32 moves the residual pass of 256-wide nets onto the tensor cores
         spec = PassSpec(layers=module.layer_sizes, activation=module.activation_name, kind=kind,
-                        dirs=dirs, fields=fields, w_fid=0.0, w_res=1.0)
+                        dirs=dirs, fields=fields, w_fid=0.0, w_res=1.0,
+                        precision=os.environ.get("PINN_B200_PRECISION", "fp32"))
         jl = JetLoss(spec, xin, None)
         _CACHE[key] = jl
     return _ResidualFunction.apply(module, jl, *module.parameters())
