@@ -372,8 +372,14 @@ def main():
         peak, bound = bf16 / 2.0, "tensor"
         peak_src = ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32 runs at half the bf16 rate)"
                     if peaks else "fallback 1.4 PFLOP/s bf16 sustained / 2")
+    # DRAM bytes per point from the committed `ncu --set full` captures of a 1,048,576-point launch
+    # (profiles/r1_*_ncu_full.csv: dram__bytes_read.sum + dram__bytes_write.sum), scaled to this launch
+    dram_per_point = {"fp32": (0.880954880e9 + 28.288754e9) / 1048576,
+                      "tf32": (52.560982e9 + 69.157116e9) / 1048576}[args.precision]
     roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": dram_per_point * (hi - lo),
+                "traffic_note": "bytes; ncu capture of a 1,048,576-point launch scaled by points",
+                "peak_source": peak_src,
                 "kernel": "pinn::jet_kernel" if args.precision == "fp32" else "pinn::jet_tc_kernel", "kernel_ms": kern_ms,
                 "flops_per_point": F, "points_per_launch": hi - lo,
                 "hbm_gbs_streaming": (hi - lo) * (w["layers"][0] + len(w["target_cols"])) * 4

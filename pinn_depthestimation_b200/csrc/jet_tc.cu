@@ -34,8 +34,15 @@ namespace pinn {
 constexpr int TC_H = 256;                  // hidden width handled by this kernel
 constexpr int TC_M = 128;                  // rows per tile
 constexpr int TC_TP = 32;                  // points per tile
-constexpr int TC_WORKERS = 256;
-constexpr int TC_THREADS = 320;
+#ifndef PINN_TC_WPS
+#define PINN_TC_WPS 4
+#endif
+constexpr int TC_WPS = PINN_TC_WPS;         // worker warps per TMEM subpartition (2 or 4)
+constexpr int TC_WORKERS = 128 * TC_WPS;
+constexpr int TC_THREADS = TC_WORKERS + 64;
+constexpr int TC_WCOLS = TC_H / TC_WPS;    // columns of a 128x256 accumulator owned by one worker warp
+constexpr int TC_WBLK = TC_WCOLS / 16;     // 16-column blocks per worker
+constexpr int TC_PARTS = TC_WORKERS / TC_H;  // worker threads per feature in the thread-per-feature phases
 constexpr int TC_STAGES = 4;
 constexpr int TC_STAGE_BYTES = 16384;
 constexpr int TC_STAGE_FLOATS = TC_STAGE_BYTES / 4;
@@ -67,7 +74,7 @@ struct TcArgs {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TC_WORKERS) : "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
@@ -237,7 +244,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int hl = i / TC_H, f = i - hl * TC_H;
     bias_s[i] = hl < NHH ? A.params[P0 + (long long)hl * PH + (long long)TC_H * TC_H + f] : 0.f;
   }
-  if (warp == 9) {
+  if (warp == TC_WORKERS / 32 + 1) {
     tmem_alloc(tmem_ptr, 512);
     tmem_relinquish();
   }
@@ -246,7 +253,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 8) {
+  if (warp == TC_WORKERS / 32) {
     // =========================================== producer ===========================================
     if (lane == 0) {
       int pc = 0, nzt = 0;
@@ -277,7 +284,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == TC_WORKERS / 32 + 1) {
     // =========================================== MMA issuer =========================================
     if (lane == 0) {
       constexpr uint32_t idesc_k = umma_idesc(TC_M, TC_H, 0, 0);
@@ -350,7 +357,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
   } else {
     // =========================================== workers ============================================
-    const int sp = warp & 3, half = warp >> 2;
+    const int sp = warp & 3, half = warp >> 2;   // `half` = which TC_WCOLS-wide column slice this warp owns
+    const int cbase = half * TC_WCOLS;
     const int m = sp * 32 + lane;          // this thread's row of the tile = its TMEM lane
     const int p = m >> 2, j = m & 3;
     const int leader = lane & ~3;
@@ -381,9 +389,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     auto t_copy = [&](float* img) {
       __syncwarp();
 #pragma unroll 4
-      for (int itc = 0; itc < 32; ++itc) {
+      for (int itc = 0; itc < TC_WCOLS / 4; ++itc) {
         const int idx = itc * 32 + lane;
-        const int q = idx >> 7, f = half * 128 + (idx & 127);
+        const int q = idx / TC_WCOLS, f = cbase + (idx % TC_WCOLS);
         const unsigned char* src = op + (f >> 2) * OP_LBO + (sp * 32 + 4 * q) * 16 + (f & 3) * 4;
         float4 v;
         v.x = *reinterpret_cast<const float*>(src);
@@ -399,9 +407,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int wtid = tid;  // workers are threads 0..255
     auto r_copy = [&](float* img) {
 #pragma unroll 8
-      for (int c = 0; c < 32; ++c)
+      for (int c = 0; c < TC_WCOLS / 4; ++c)
         reinterpret_cast<float4*>(img)[(size_t)c * TC_WORKERS + wtid] =
-            *reinterpret_cast<const float4*>(op + (half * 32 + c) * OP_LBO + m * 16);
+            *reinterpret_cast<const float4*>(op + (cbase / 4 + c) * OP_LBO + m * 16);
     };
     auto r_load = [&](const float* img, int b, float (&v)[16]) {
 #pragma unroll
@@ -446,8 +454,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       // ---------------- layer 0 (d -> 256) on the FP32 pipes ----------------
       {
         const int dircol = (j >= 1 && j - 1 < D.n_dirs) ? D.dir_cols[j - 1] : -1;
-        for (int b = 0; b < 8; ++b) {
-          const int f0 = half * 128 + b * 16;
+        for (int b = 0; b < TC_WBLK; ++b) {
+          const int f0 = cbase + b * 16;
           float z[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -478,8 +486,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         TCT(2)
         const float* bias_l = (l - 1 < TC_MAX_HH) ? bias_s + (l - 1) * TC_H
                                                   : A.params + P0 + (long long)(l - 1) * PH + (long long)TC_H * TC_H;
-        for (int b = 0; b < 8; ++b) {
-          const int f0 = half * 128 + b * 16;
+        for (int b = 0; b < TC_WBLK; ++b) {
+          const int f0 = cbase + b * 16;
           float z[16];
           tmem_ld16(tmem_row + (uint32_t)f0, z);
           // value rows: a = tanh(z + b); tangent rows: s * zdot with s = 1 - a^2 of the point's value row
@@ -509,19 +517,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       worker_bar();
       // ---------------- last layer (256 -> o) on the FP32 pipes ----------------
       {
+        constexpr int NCS = TC_WORKERS / 128, NCI = 8 / NCS;
         const int mm = tid & 127, cs = tid >> 7;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float acc[NCI];
+#pragma unroll
+        for (int ci = 0; ci < NCI; ++ci) acc[ci] = 0.f;
         for (int q = 0; q < TC_H / 4; ++q) {
           const float4 a = *reinterpret_cast<const float4*>(op + q * OP_LBO + mm * 16);
 #pragma unroll
-          for (int ci = 0; ci < 4; ++ci) {
-            const float4 w = *reinterpret_cast<const float4*>(wls + (cs + 2 * ci) * TC_H + 4 * q);
+          for (int ci = 0; ci < NCI; ++ci) {
+            const float4 w = *reinterpret_cast<const float4*>(wls + (cs + NCS * ci) * TC_H + 4 * q);
             acc[ci] = fmaf(a.x, w.x, fmaf(a.y, w.y, fmaf(a.z, w.z, fmaf(a.w, w.w, acc[ci]))));
           }
         }
 #pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
-          const int c = cs + 2 * ci;
+        for (int ci = 0; ci < NCI; ++ci) {
+          const int c = cs + NCS * ci;
           float v = acc[ci];
           if ((mm & 3) == 0 && c < o) v += A.params[poffL + (long long)TC_H * o + c];
           outs[mm * 8 + c] = c < o ? v : 0.f;
@@ -550,12 +561,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       // =============================== reverse ===============================
       // ---- last layer: dW_last[c][f] = sum_m zbar[m][c] * A[m][f] (thread per feature), db_last ----
       {
-        const int f = tid;
+        const int f = tid & (TC_H - 1), part = tid / TC_H;
         float acc[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[c] = 0.f;
         const unsigned char* ap = op + (f >> 2) * OP_LBO + (f & 3) * 4;
-        for (int mm = 0; mm < TC_M; ++mm) {
+        for (int mm = part * (TC_M / TC_PARTS); mm < (part + 1) * (TC_M / TC_PARTS); ++mm) {
           const float a = *reinterpret_cast<const float*>(ap + mm * 16);
           const float4 z0 = *reinterpret_cast<const float4*>(outs + mm * 8);
           const float4 z1 = *reinterpret_cast<const float4*>(outs + mm * 8 + 4);
@@ -579,8 +590,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         float zl[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) zl[c] = outs[m * 8 + c];
-        for (int b = 0; b < 8; ++b) {
-          const int f0 = half * 128 + b * 16;
+        for (int b = 0; b < TC_WBLK; ++b) {
+          const int f0 = cbase + b * 16;
           float ab[16], act[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -609,11 +620,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const long long poff = P0 + (long long)(l - 1) * PH;
         // bias gradient: sum over the value rows of Zbar_l (thread per feature)
         {
-          const int f = tid;
+          const int f = tid & (TC_H - 1), part = tid / TC_H;
           const unsigned char* zp = op + (f >> 2) * OP_LBO + (f & 3) * 4;
           float s = 0.f;
 #pragma unroll 8
-          for (int pp = 0; pp < TC_TP; ++pp) s += *reinterpret_cast<const float*>(zp + (4 * pp) * 16);
+          for (int pp = part * (TC_TP / TC_PARTS); pp < (part + 1) * (TC_TP / TC_PARTS); ++pp)
+            s += *reinterpret_cast<const float*>(zp + (4 * pp) * 16);
           atomicAdd(A.grad + poff + (long long)TC_H * TC_H + f, s);
         }
         signal_ready();
@@ -627,10 +639,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const int row = h * 128 + sp * 32 + g * 16 + (lane >> 2);
-            float* grow = A.grad + poff + (long long)row * TC_H + half * 128 + 2 * (lane & 3);
-            const uint32_t ta = tmem_base + ((uint32_t)(sp * 32 + g * 16) << 16) + (uint32_t)(h * 256 + half * 128);
+            float* grow = A.grad + poff + (long long)row * TC_H + cbase + 2 * (lane & 3);
+            const uint32_t ta = tmem_base + ((uint32_t)(sp * 32 + g * 16) << 16) + (uint32_t)(h * 256 + cbase);
 #pragma unroll
-            for (int cb = 0; cb < 4; ++cb) {
+            for (int cb = 0; cb < TC_WCOLS / 32; ++cb) {
               float v[16];
               tmem_ld_16x256b_x4(ta + (uint32_t)(cb * 32), v);
 #pragma unroll
@@ -650,10 +662,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           r_load(rimg, 0, act);   // issued before the wait: the loads overlap the adjoint MMA
           wait_mma();
           TCT(9)
-          for (int b = 0; b < 8; ++b) {
-            const int f0 = half * 128 + b * 16;
+          for (int b = 0; b < TC_WBLK; ++b) {
+            const int f0 = cbase + b * 16;
             float ab[16];
-            if (b < 7) r_load(rimg, b + 1, nxt);
+            if (b < TC_WBLK - 1) r_load(rimg, b + 1, nxt);
             tmem_ld16(tmem_row + (uint32_t)f0, ab);
             adjoint(ab, act);
             store_op(f0, ab);
@@ -674,12 +686,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       // ---- layer 0: dW0[f][c], db0[f] from Zbar_0 (thread per feature) ----
       {
-        const int f = tid;
+        const int f = tid & (TC_H - 1), part = tid / TC_H;
         const unsigned char* zp = op + (f >> 2) * OP_LBO + (f & 3) * 4;
         float acc[8], tj[3] = {0.f, 0.f, 0.f}, sb = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-        for (int pp = 0; pp < TC_TP; ++pp) {
+        for (int pp = part * (TC_TP / TC_PARTS); pp < (part + 1) * (TC_TP / TC_PARTS); ++pp) {
           const float z0 = *reinterpret_cast<const float*>(zp + (4 * pp) * 16);
           sb += z0;
 #pragma unroll
@@ -715,7 +727,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 9) tmem_dealloc(tmem_base, 512);
+  if (warp == TC_WORKERS / 32 + 1) tmem_dealloc(tmem_base, 512);
   if (tid < PINN_NSUMS && A.sums && red[tid] != 0.0) atomicAdd(A.sums + tid, red[tid]);
 }
 
