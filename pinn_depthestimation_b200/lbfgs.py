@@ -29,20 +29,32 @@ from . import _cabi
 # ------------------------------------------------------------------------------------------------
 # host-side scalar logic (pure Python floats; unit-tested on CPU against torch's own functions)
 # ------------------------------------------------------------------------------------------------
+def _ieee_div(a, b):
+    """a / b with IEEE semantics (inf / nan instead of ZeroDivisionError), like torch's tensor maths."""
+    try:
+        return a / b
+    except ZeroDivisionError:
+        if a == 0 or a != a:
+            return math.nan
+        return math.copysign(math.inf, a) * math.copysign(1.0, b)
+
+
 def cubic_interpolate(x1, f1, g1, x2, f2, g2, bounds=None):
-    """Minimiser of the cubic through (x1,f1,g1), (x2,f2,g2) clipped to bounds (lbfgs.py:12-37)."""
+    """Minimiser of the cubic through (x1,f1,g1), (x2,f2,g2) clipped to bounds (lbfgs.py:12-37).
+    A collapsed bracket (x1 == x2) yields inf/nan intermediates and falls through to bisection or the
+    clipping, exactly as torch's 0-d tensor arithmetic does."""
     if bounds is not None:
         xmin_bound, xmax_bound = bounds
     else:
         xmin_bound, xmax_bound = (x1, x2) if x1 <= x2 else (x2, x1)
-    d1 = g1 + g2 - 3 * (f1 - f2) / (x1 - x2)
+    d1 = g1 + g2 - 3 * _ieee_div(f1 - f2, x1 - x2)
     d2_square = d1 * d1 - g1 * g2
     if d2_square >= 0:
         d2 = math.sqrt(d2_square)
         if x1 <= x2:
-            min_pos = x2 - (x2 - x1) * ((g2 + d2 - d1) / (g2 - g1 + 2 * d2))
+            min_pos = x2 - (x2 - x1) * _ieee_div(g2 + d2 - d1, g2 - g1 + 2 * d2)
         else:
-            min_pos = x1 - (x1 - x2) * ((g1 + d2 - d1) / (g1 - g2 + 2 * d2))
+            min_pos = x1 - (x1 - x2) * _ieee_div(g1 + d2 - d1, g1 - g2 + 2 * d2)
         return min(max(min_pos, xmin_bound), xmax_bound)
     return (xmin_bound + xmax_bound) / 2.0
 

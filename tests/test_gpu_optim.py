@@ -254,3 +254,28 @@ def test_trainer_runs_the_reference_schedule_and_log_format(tmp_path):
     torch.save(model.dnn, tmp_path / "model.pth")
     again = torch.load(tmp_path / "model.pth", weights_only=False)
     assert torch.equal(again.flat_params(), model.dnn.flat_params())
+
+
+def test_train_main_script_runs_a_reference_style_config(tmp_path):
+    """python -m pinn_depthestimation_b200.train_main on a config with the reference's key layout
+    (config_CMB_h.json), synthetic points standing in for the unshipped .mat file."""
+    import json
+    from pinn_depthestimation_b200 import train_main
+    cfg = {
+        "layers": {"input_features": 2, "hidden_layers": 5, "hidden_width": 20, "output_features": 3,
+                   "dropout_rate": 0.0, "init_type": "xavier"},
+        "adam_optimizer": {"max_it": 20, "learning_rate": 1e-3, "scheduler_step_size": 10000,
+                           "scheduler_gamma": 0.8},
+        "lbfgs_optimizer": {"max_it": 5, "learning_rate": 1, "max_evaluation": 8, "history_size": 100,
+                            "tolerance_grad": 1e-5, "tolerance_change": 1e-7, "line_search_fn": "strong_wolfe"},
+        "loss": {"weight_fid_loss": 1, "weight_res_loss": 1},
+        "data": {"file": "unused.mat", "inputs": {"x": {"requires_grad": ["true"]}, "y": {"requires_grad": ["true"]}},
+                 "trues": ["U", "V"], "unknowns": ["h"]},
+        "data_test": {"x_min": 25.0, "x_max": 33.0, "y_min": -13.0, "y_max": 13.0},
+    }
+    path = tmp_path / "config.json"
+    path.write_text(json.dumps(cfg))
+    model = train_main.main(["--config", str(path), "--synthetic", "300", "--log-dir", str(tmp_path / "log")])
+    assert (tmp_path / "log" / "model.pth").exists()
+    assert (tmp_path / "log" / "log.txt").exists()
+    assert model.history[-1][3] < model.history[0][3]

@@ -122,3 +122,13 @@ def test_strong_wolfe_follows_torch_branch_for_branch(kind, seed):
     assert abs(mt - float(rt)) <= 1e-9 * max(1.0, abs(mt))
     assert abs(mf - rf) <= 1e-9 * max(1.0, abs(mf))
     np.testing.assert_allclose(mg, rg.numpy(), rtol=1e-9, atol=1e-12)
+
+
+def test_cubic_interpolate_collapsed_bracket_behaves_like_torch():
+    """x1 == x2: torch's tensor arithmetic gives inf/nan and the result degenerates; no exception."""
+    tt = lambda v: torch.tensor(v, dtype=torch.float64)
+    for (x1, f1, g1, x2, f2, g2) in [(0.5, 1.0, -1.0, 0.5, 1.0, 0.3), (0.5, 1.0, -1.0, 0.5, 2.0, 0.3),
+                                     (0.2, 3.0, 0.0, 0.2, 1.0, 0.0)]:
+        ref = tl._cubic_interpolate(tt(x1), f1, tt(g1), tt(x2), f2, tt(g2))
+        mine = cubic_interpolate(x1, f1, g1, x2, f2, g2)
+        assert (mine != mine and float(ref) != float(ref)) or abs(float(ref) - mine) <= 1e-12
