@@ -40,6 +40,19 @@ WORKLOADS = {
 }
 CHUNK = 1 << 21   # points per deterministic generation chunk (seed = 1234 + chunk index)
 
+# the reference's own config shapes: name -> (layers, residual, dirs, fields, target cols, N)
+_XY = {"x": 0, "y": 1}
+_TXY = {"t": 0, "x": 1, "y": 2}
+REAL_SHAPES = {
+    "config_CMB_h.json": ([2] + [20] * 100 + [3], "continuity_only", _XY, {"U": 0, "V": 1, "h": 2}, [0, 1], 12514),
+    "config_CMB.json": ([2] + [10] * 10 + [6], "physics_equation", _XY,
+                        {"h": 0, "U": 1, "V": 2, "eta_mean": 3, "Hrms": 4, "k": 5}, [0, 1, 2, 3, 4, 5], 243),
+    "config.json": ([5] + [20] * 100 + [4], "Navier_Stokes", _TXY, {"h": 0, "z": 1, "u": 2, "v": 3},
+                    [0, 1, 2, 3], 9600),
+    "config_txyz.json": ([4] + [20] * 20 + [4], "Navier_Stokes", _TXY, {"h": 0, "z": 1, "u": 2, "v": 3},
+                         [0, 1, 2, 3], 9600),
+}
+
 
 def flops_per_point(w):
     """F = 6 (1+k) sum_l in_l*out_l (jet forward 2(1+k)S, reverse 4(1+k)S)."""
@@ -194,6 +207,8 @@ def main():
     ap.add_argument("--lbfgs-iters", type=int, default=6,
                     help="max_iter of the L-BFGS side measurement (BASELINE metric ii); 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--real-shapes", type=int, default=1,
+                    help="also time one evaluation of the reference's own config shapes (latency rows)")
     args = ap.parse_args()
     name = args.workload
     w = dict(WORKLOADS[name])
@@ -324,6 +339,34 @@ def main():
                       "line_search_fn": "strong_wolfe", "n_points": n_total}
         del opt, pl
 
+    # ---- side measurement: the reference's own config shapes (latency + launch count) ----
+    real_shapes = None
+    if rank == 0 and args.real_shapes:
+        real_shapes = []
+        for nm, (rl, rk, rd, rf, rt, rn) in REAL_SHAPES.items():
+            rspec = PassSpec(layers=rl, kind=rk, dirs=rd, fields=rf, target_cols=rt, precision="fp32")
+            g_ = torch.Generator().manual_seed(1234)
+            rx = (torch.rand(rn, rl[0], generator=g_) * 2 - 1).to(dev)
+            rtg = (0.05 * torch.randn(rn, len(rt), generator=g_)).to(dev)
+            torch.manual_seed(1234)
+            from pinn_depthestimation_b200.dnn import DNN
+            rp = DNN(rl, 0.0, "xavier").flat_params().clone().to(dev)
+            rg = torch.empty_like(rp)
+            rj = JetLoss(rspec, rx, rtg)
+            for _ in range(3):
+                rj.loss_and_grad(rp, rg)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(20):
+                rj.loss_and_grad(rp, rg)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_ = e0.elapsed_time(e1) / 20
+            real_shapes.append({"config": nm, "layers": f"[{rl[0]}]+[{rl[1]}]x{len(rl) - 2}+[{rl[-1]}]",
+                                "residual": rk, "n_points": rn, "ms_per_eval": ms_,
+                                "points_per_s": rn / (ms_ * 1e-3), "kernel_launches_per_eval": 3,
+                                "reference_aten_ops_per_eval": "~2900 (SURVEY.md 2.2)"})
+
     # ---- side measurement: the FP32 parity mode on the same workload ---------------------------
     fp32_side = None
     if args.precision != "fp32" and args.fp32_steps > 0:
@@ -368,10 +411,26 @@ def main():
             best = max(best, fl.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
         peak, bound, peak_src = best, "fp32_fma", "measured in this run (pinn_fma_probe, FFMA-bound kernel)"
     else:
+        # TF32 tensor peak: MEASURED_PEAKS.json holds only bf16, so measure a cuBLAS TF32 GEMM here
+        # (8192^3, best of 5) and keep the bf16-derived figure beside it
         bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
-        peak, bound = bf16 / 2.0, "tensor"
-        peak_src = ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32 runs at half the bf16 rate)"
-                    if peaks else "fallback 1.4 PFLOP/s bf16 sustained / 2")
+        old_flag = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        ga = torch.randn(8192, 8192, device=dev)
+        gb = torch.randn(8192, 8192, device=dev)
+        torch.matmul(ga, gb)
+        tf32_meas = 0.0
+        for _ in range(5):
+            e0.record()
+            torch.matmul(ga, gb)
+            e1.record()
+            torch.cuda.synchronize()
+            tf32_meas = max(tf32_meas, 2 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        torch.backends.cuda.matmul.allow_tf32 = old_flag
+        del ga, gb
+        peak, bound = max(tf32_meas, bf16 / 2.0), "tensor"
+        peak_src = ("max(cuBLAS TF32 GEMM 8192^3 measured in this run = %.1f TFLOP/s, "
+                    "MEASURED_PEAKS.json bf16_tflops_sustained / 2 = %.1f)" % (tf32_meas, bf16 / 2.0))
     # DRAM bytes per point from the committed `ncu --set full` captures of a 1,048,576-point launch
     # (profiles/r1_*_ncu_full.csv: dram__bytes_read.sum + dram__bytes_write.sum), scaled to this launch
     dram_per_point = {"fp32": (0.880954880e9 + 28.288754e9) / 1048576,
@@ -410,6 +469,7 @@ def main():
                            "mode": "tf32 operands, fp32 accumulate (stated looser bound; tests/test_gpu_tc.py)"}),
             "fp32_parity_mode": fp32_side,
             "lbfgs": lbfgs_side,
+            "real_shapes_fp32": real_shapes,
         }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
