@@ -203,7 +203,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint64_t* mma_done = op_ready + 1;
   uint64_t* slab_ready = mma_done + 1;
   uint64_t* zt_ready = slab_ready + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(zt_ready + 1);
+  uint64_t* mma_done_b = zt_ready + 1;   // weight-gradient accumulator (TMEM columns 256..511) complete
+  uint64_t* rb_free = mma_done_b + 1;    // ... and drained by the workers
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(rb_free + 1);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const int my_tiles = (A.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   float* slab = A.slab + (long long)blockIdx.x * A.slab_stride;
   float* slab_r = slab + (size_t)(L - 2) * TC_M * TC_H;      // thread-private row images (reverse loads)
-  float* zt = slab_r + (size_t)(L - 2) * TC_M * TC_H;        // T-image of the current Zbar
+  float* zt = slab_r + (size_t)(L - 2) * TC_M * TC_H;        // two T-images of Zbar (layer parity), split by feature half
   const long long P0 = (long long)d * TC_H + TC_H;               // params of layer 0
   const long long PH = (long long)TC_H * TC_H + TC_H;            // params of a hidden->hidden layer
   const long long poffL = P0 + (long long)NHH * PH;              // params offset of the last layer
@@ -229,6 +231,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     mbar_init(mma_done, 1);
     mbar_init(slab_ready, TC_WORKERS);
     mbar_init(zt_ready, TC_WORKERS);
+    mbar_init(mma_done_b, 1);
+    mbar_init(rb_free, TC_WORKERS);
     mbar_fence_init();
   }
   if (tid < PINN_NSUMS) red[tid] = 0.0;
@@ -270,17 +274,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             load(A.packed + (size_t)hl * 2 * TC_H * TC_H + (size_t)c * TC_STAGE_FLOATS);
         if (BWD) {
           mbar_wait(slab_ready, (uint32_t)(it & 1));  // this tile's slab entries are written and fenced
-          for (int l = L - 2; l >= 1; --l) {
-            mbar_wait(zt_ready, (uint32_t)(nzt & 1));  // Zbar_l has been spilled as a T-image
-            ++nzt;
-            for (int c = 0; c < TC_SCHUNKS; ++c) {     // 16 rows per chunk: Zbar_l^T then A_in^T (= output of l-1)
-              load(zt + (size_t)c * TC_STAGE_FLOATS);
-              load(slab + (size_t)(l - 1) * TC_M * TC_H + (size_t)c * TC_STAGE_FLOATS);
+          // one weight-gradient half job = 128 Zbar features x 256 A_in features over the tile's 128 rows:
+          // per 32 rows one stage of Zbar^T (two 16-row half-chunks) and two stages of A_in^T
+          auto load_dw_half = [&](int l, int h) {
+            const float* zsrc = zt + (size_t)(l & 1) * TC_M * TC_H + (size_t)h * (TC_M * TC_H / 2);
+            const float* asrc = slab + (size_t)(l - 1) * TC_M * TC_H;
+            for (int g = 0; g < 4; ++g) {
+              load(zsrc + (size_t)g * TC_STAGE_FLOATS);
+              load(asrc + (size_t)(2 * g) * TC_STAGE_FLOATS);
+              load(asrc + (size_t)(2 * g + 1) * TC_STAGE_FLOATS);
             }
-            for (int c = 0; c < TC_WCHUNKS; ++c)
+          };
+          for (int l = L - 2; l >= 1; --l) {
+            for (int c = 0; c < TC_WCHUNKS; ++c)       // adjoint job of layer l
               load(A.packed + (size_t)(l - 1) * 2 * TC_H * TC_H + (size_t)TC_H * TC_H +
                    (size_t)c * TC_STAGE_FLOATS);
+            if (l < L - 2) load_dw_half(l + 1, 1);
+            mbar_wait(zt_ready, (uint32_t)(nzt & 1));  // Zbar_l has been spilled as a T-image
+            ++nzt;
+            load_dw_half(l, 0);
           }
+          load_dw_half(1, 1);
         }
       }
     }
@@ -290,7 +304,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       constexpr uint32_t idesc_k = umma_idesc(TC_M, TC_H, 0, 0);
       const uint32_t op_addr = smem_u32(op);
       const uint32_t ring_addr = smem_u32(ring);
-      int cc = 0, jobs = 0;
+      int cc = 0, jobs = 0, nB = 0;
       auto wait_ready = [&]() {
         mbar_wait(op_ready, (uint32_t)(jobs & 1));
         ++jobs;
@@ -321,37 +335,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           gemm_k();
         }
         if (BWD) {
-          for (int l = L - 2; l >= 1; --l) {
-            // weight gradient: D_h[128 Zbar features x 256 A_in features] += sum over rows; both operands are
-            // 16-row chunks of T-images, i.e. K-major with K = row (A chunk in stage sa, B chunk in stage sb)
-            wait_ready();
-            for (int c = 0; c < TC_SCHUNKS; ++c) {
-              const int sa = cc % TC_STAGES, sb = (cc + 1) % TC_STAGES;
-              mbar_wait(&full[sa], (uint32_t)((cc / TC_STAGES) & 1));
-              mbar_wait(&full[sb], (uint32_t)(((cc + 1) / TC_STAGES) & 1));
+          // weight-gradient half job into TMEM columns 256..511: both operands are K-major with K = row
+          auto dw_half = [&]() {
+            if (nB > 0) {
+              mbar_wait(rb_free, (uint32_t)((nB - 1) & 1));   // the previous half has been drained
               tc_fence_after();
-#pragma unroll
-              for (int kk = 0; kk < 2; ++kk) {
-                const int kstep = c * 2 + kk;  // 8 rows per MMA = two 16-byte K chunks
-                const uint64_t bd = umma_desc(ring_addr + (uint32_t)sb * TC_STAGE_BYTES + (uint32_t)kk * 2u * (TC_H * 16),
-                                              TC_H * 16, 128);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                  const uint64_t ad = umma_desc(ring_addr + (uint32_t)sa * TC_STAGE_BYTES + (uint32_t)h * (128u * 16u) +
-                                                    (uint32_t)kk * 2u * (TC_H * 16),
-                                                TC_H * 16, 128);
-                  umma_tf32(tmem_base + (uint32_t)h * 256u, ad, bd, idesc_k, kstep > 0 ? 1u : 0u);
-                }
-              }
-              umma_commit(&empty[sa]);
-              umma_commit(&empty[sb]);
-              cc += 2;
             }
-            umma_commit(mma_done);
-            // adjoint of the layer input
-            wait_ready();
-            gemm_k();
+            ++nB;
+            for (int g = 0; g < 4; ++g) {
+              const int sz = cc % TC_STAGES;
+              mbar_wait(&full[sz], (uint32_t)((cc / TC_STAGES) & 1));
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const int ca = cc + 1 + i, sa = ca % TC_STAGES;
+                mbar_wait(&full[sa], (uint32_t)((ca / TC_STAGES) & 1));
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                  const int kstep = g * 4 + i * 2 + kk;   // 8 rows per MMA
+                  const uint64_t ad = umma_desc(ring_addr + (uint32_t)sz * TC_STAGE_BYTES + (uint32_t)i * 8192u +
+                                                    (uint32_t)kk * 2u * (128u * 16u),
+                                                128 * 16, 128);
+                  const uint64_t bd = umma_desc(ring_addr + (uint32_t)sa * TC_STAGE_BYTES + (uint32_t)kk * 2u * (TC_H * 16),
+                                                TC_H * 16, 128);
+                  umma_tf32(tmem_base + 256u, ad, bd, idesc_k, kstep > 0 ? 1u : 0u);
+                }
+                umma_commit(&empty[sa]);
+              }
+              umma_commit(&empty[sz]);
+              cc += 3;
+            }
+            umma_commit(mma_done_b);
+          };
+          for (int l = L - 2; l >= 1; --l) {
+            wait_ready();                      // Zbar_l is in the operand image, columns 0..255 are drained
+            gemm_k();                          // adjoint of the layer input
+            if (l < L - 2) dw_half();          // layer l+1, features 128..255
+            dw_half();                         // layer l,   features 0..127
           }
+          dw_half();                           // layer 1,   features 128..255
         }
       }
     }
@@ -364,7 +386,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int leader = lane & ~3;
     const uint32_t tmem_row = tmem_base + ((uint32_t)(sp * 32) << 16);
     const float inv_cnt = (kind == PINN_RES_CONT_ONLY && A.mask_count) ? 1.0f / *A.mask_count : 0.f;
-    int mj = 0;  // MMA jobs waited for
+    int mj = 0;   // adjoint / forward MMA jobs waited for
+    int nbw = 0;  // weight-gradient half jobs drained
     TCT_DECL
     auto wait_mma = [&]() {
       mbar_wait(mma_done, (uint32_t)(mj & 1));
@@ -386,7 +409,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // T-image (row-transposed, 16-row chunks): (row m, feature f) at float (m/16)*4096 + ((m%16)/4)*1024 + f*4 + m%4.
     // Each warp transposes the 32 rows x 128 features it owns out of the operand image: 4 conflict-free
     // LDS.32 (the 4 rows of a quad) -> one coalesced 16-byte store per feature.
-    auto t_copy = [&](float* img) {
+    auto t_copy = [&](float* img, bool split) {
       __syncwarp();
 #pragma unroll 4
       for (int itc = 0; itc < TC_WCOLS / 4; ++itc) {
@@ -398,8 +421,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         v.y = *reinterpret_cast<const float*>(src + 16);
         v.z = *reinterpret_cast<const float*>(src + 32);
         v.w = *reinterpret_cast<const float*>(src + 48);
-        *reinterpret_cast<float4*>(img + (size_t)(2 * sp + (q >> 2)) * TC_STAGE_FLOATS + (size_t)(q & 3) * (TC_H * 4) +
-                                   (size_t)f * 4) = v;
+        const size_t dst = split ? (size_t)(f >> 7) * (TC_M * TC_H / 2) + (size_t)(2 * sp + (q >> 2)) * (TC_STAGE_FLOATS / 2) +
+                                       (size_t)(q & 3) * (TC_H * 2) + (size_t)(f & 127) * 4
+                                 : (size_t)(2 * sp + (q >> 2)) * TC_STAGE_FLOATS + (size_t)(q & 3) * (TC_H * 4) + (size_t)f * 4;
+        *reinterpret_cast<float4*>(img + dst) = v;
       }
     };
     // R-image: thread-private float4 slots [(block b, q)][worker thread] (coalesced), for the reverse loads;
@@ -477,7 +502,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       signal_ready();
       if (BWD && NHH >= 1) {
         r_copy(slab_r);
-        t_copy(slab);
+        t_copy(slab, false);
       }
       TCT(3)
       // ---------------- hidden layers 1..L-2 on the tensor cores ----------------
@@ -503,7 +528,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (l < L - 2) signal_ready();
         if (BWD && l <= L - 3) {
           r_copy(slab_r + (size_t)l * TC_M * TC_H);
-          t_copy(slab + (size_t)l * TC_M * TC_H);
+          t_copy(slab + (size_t)l * TC_M * TC_H, false);
         }
         TCT(3)
       }
@@ -609,52 +634,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           store_op(f0, ab);
         }
       }
-      t_copy(zt);
+      t_copy(zt + (size_t)((L - 2) & 1) * TC_M * TC_H, true);
       __threadfence();
       fence_async_proxy();
       mbar_arrive(zt_ready);
       worker_bar();
       TCT(5)
-      // ---- hidden layers L-2 .. 1 ----
-      for (int l = L - 2; l >= 1; --l) {
-        const long long poff = P0 + (long long)(l - 1) * PH;
-        // bias gradient: sum over the value rows of Zbar_l (thread per feature)
-        {
-          const int f = tid & (TC_H - 1), part = tid / TC_H;
-          const unsigned char* zp = op + (f >> 2) * OP_LBO + (f & 3) * 4;
-          float s = 0.f;
+      // ---- hidden layers L-2 .. 1, software-pipelined ----
+      //   tensor core: adjoint job of layer l (TMEM columns 0..255), weight-gradient halves (columns 256..511)
+      //   workers:     adjoint epilogue of layer l | drain half 1 of layer l+1 | spill Zbar_{l-1}^T | drain half 0 of layer l
+      // The only serial chain is adjoint epilogue -> adjoint MMA -> adjoint epilogue; the drains hide behind it.
+      auto bias_grad = [&](int l) {   // sum over the value rows of Zbar_l (thread per feature)
+        const int f = tid & (TC_H - 1), part = tid / TC_H;
+        const unsigned char* zp = op + (f >> 2) * OP_LBO + (f & 3) * 4;
+        float sacc = 0.f;
 #pragma unroll 8
-          for (int pp = part * (TC_TP / TC_PARTS); pp < (part + 1) * (TC_TP / TC_PARTS); ++pp)
-            s += *reinterpret_cast<const float*>(zp + (4 * pp) * 16);
-          atomicAdd(A.grad + poff + (long long)TC_H * TC_H + f, s);
-        }
-        signal_ready();
-        TCT(6)
-        // weight gradient: drain D_0 / D_1 (rows = Zbar feature n, columns = A_in feature k)
-        wait_mma();
-        TCT(7)
-        // 16x256b loads: the 4 lanes of a quad hold 8 consecutive columns of one row, so every RED
-        // instruction updates full 32-byte sectors (8 rows x 32 B) instead of 32 half-filled ones
-        for (int h = 0; h < 2; ++h) {
+        for (int pp = part * (TC_TP / TC_PARTS); pp < (part + 1) * (TC_TP / TC_PARTS); ++pp)
+          sacc += *reinterpret_cast<const float*>(zp + (4 * pp) * 16);
+        atomicAdd(A.grad + P0 + (long long)(l - 1) * PH + (long long)TC_H * TC_H + f, sacc);
+      };
+      // drain TMEM columns 256..511 = dW rows [128h, 128h+128) of layer l.  16x256b loads: the 4 lanes of a
+      // quad hold 8 consecutive columns of one row, so every RED instruction updates full 32-byte sectors
+      auto drain = [&](int l, int h) {
+        mbar_wait(mma_done_b, (uint32_t)(nbw & 1));
+        ++nbw;
+        tc_fence_after();
+        const long long poff = P0 + (long long)(l - 1) * PH;
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const int row = h * 128 + sp * 32 + g * 16 + (lane >> 2);
-            float* grow = A.grad + poff + (long long)row * TC_H + cbase + 2 * (lane & 3);
-            const uint32_t ta = tmem_base + ((uint32_t)(sp * 32 + g * 16) << 16) + (uint32_t)(h * 256 + cbase);
+        for (int g = 0; g < 2; ++g) {
+          const int row = h * 128 + sp * 32 + g * 16 + (lane >> 2);
+          float* grow = A.grad + poff + (long long)row * TC_H + cbase + 2 * (lane & 3);
+          const uint32_t ta = tmem_base + ((uint32_t)(sp * 32 + g * 16) << 16) + (uint32_t)(256 + cbase);
 #pragma unroll
-            for (int cb = 0; cb < TC_WCOLS / 32; ++cb) {
-              float v[16];
-              tmem_ld_16x256b_x4(ta + (uint32_t)(cb * 32), v);
+          for (int cb = 0; cb < TC_WCOLS / 32; ++cb) {
+            float v[16];
+            tmem_ld_16x256b_x4(ta + (uint32_t)(cb * 32), v);
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                red_add_v2(grow + cb * 32 + 8 * u, v[4 * u], v[4 * u + 1]);
-                red_add_v2(grow + 8 * TC_H + cb * 32 + 8 * u, v[4 * u + 2], v[4 * u + 3]);
-              }
+            for (int u = 0; u < 4; ++u) {
+              red_add_v2(grow + cb * 32 + 8 * u, v[4 * u], v[4 * u + 1]);
+              red_add_v2(grow + 8 * TC_H + cb * 32 + 8 * u, v[4 * u + 2], v[4 * u + 3]);
             }
           }
         }
-        TCT(8)
-        signal_ready();
+        tc_fence_before();
+        mbar_arrive(rb_free);
+      };
+      bias_grad(L - 2);
+      signal_ready();                       // adjoint job of layer L-2 may start
+      TCT(6)
+      for (int l = L - 2; l >= 1; --l) {
         // adjoint through the activation of layer l-1 -> Zbar_{l-1} in place
         {
           const float* rimg = slab_r + (size_t)(l - 1) * TC_M * TC_H;
@@ -673,17 +701,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             for (int i = 0; i < 16; ++i) act[i] = nxt[i];
           }
         }
-        TCT(10)
         tc_fence_before();
+        worker_bar();                       // Zbar_{l-1} complete in the operand image
+        TCT(10)
         if (l > 1) {
-          t_copy(zt);                       // Zbar_{l-1}^T feeds the next weight-gradient job
+          bias_grad(l - 1);
+          signal_ready();                   // adjoint job of layer l-1 may start
+        }
+        TCT(6)
+        if (l < L - 2) drain(l + 1, 1);
+        TCT(8)
+        if (l > 1) {
+          // Zbar_{l-1}^T feeds the weight-gradient jobs of layer l-1.  Its buffer (layer parity) was last read
+          // by the half-1 job of layer l+1, which the drain above has just seen complete.
+          t_copy(zt + (size_t)((l - 1) & 1) * TC_M * TC_H, true);
           __threadfence();
           fence_async_proxy();
           mbar_arrive(zt_ready);
         }
-        worker_bar();
         TCT(11)
+        drain(l, 0);
+        TCT(7)
       }
+      drain(1, 1);
+      worker_bar();
+      TCT(8)
       // ---- layer 0: dW0[f][c], db0[f] from Zbar_0 (thread per feature) ----
       {
         const int f = tid & (TC_H - 1), part = tid / TC_H;
@@ -754,7 +796,7 @@ __global__ void pack_tc_kernel(const __grid_constant__ pinn_desc_t D, const floa
 // --------------------------------------------------------------------------------------- host side
 constexpr size_t tc_smem_bytes() {
   return (size_t)OP_BYTES + (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)TC_H * 8 * 4 + (size_t)8 * TC_H * 4 +
-         (size_t)TC_M * 8 * 4 + (size_t)TC_TP * 8 * 4 + (size_t)TC_MAX_HH * TC_H * 4 + PINN_NSUMS * 8 + (2 * TC_STAGES + 4) * 8 + 16;
+         (size_t)TC_M * 8 * 4 + (size_t)TC_TP * 8 * 4 + (size_t)TC_MAX_HH * TC_H * 4 + PINN_NSUMS * 8 + (2 * TC_STAGES + 6) * 8 + 16;
 }
 
 // Can this description run on the tensor-core kernel?  (otherwise the caller reports UNSUPPORTED)
@@ -779,7 +821,7 @@ int tc_workspace(const pinn_desc_t* D, long long n_points, int sms, size_t* pack
   if (g < 1) g = 1;
   *grid = (int)g;
   *packed_bytes = (size_t)(L - 2) * 2 * TC_H * TC_H * 4;
-  *slab_stride = (long long)(2 * (L - 2) + 1) * TC_M * TC_H;   // T- and R-images of (L-2) layer outputs + Zbar spill
+  *slab_stride = (long long)(2 * (L - 2) + 2) * TC_M * TC_H;   // T- and R-images of (L-2) layer outputs + 2 Zbar spills
   *slab_bytes = (size_t)g * (size_t)(*slab_stride) * 4;
   return PINN_OK;
 }
