@@ -59,7 +59,8 @@ class EvalArgs(C.Structure):
     ]
 
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpinn_b200.so")
+# PINN_B200_LIB selects another build of the same library (e.g. the -DPINN_TC_DEBUG cycle-counter build)
+LIB_PATH = os.environ.get("PINN_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpinn_b200.so")
 
 # every symbol include/pinn_b200.h declares: name -> (restype, argtypes)
 _P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float

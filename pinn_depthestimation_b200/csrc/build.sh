@@ -2,7 +2,7 @@
 # Builds libpinn_b200.so in-tree for sm_100a (cross-compiles without a GPU).
 set -euo pipefail
 here="$(cd "$(dirname "$0")" && pwd)"
-out="$here/../libpinn_b200.so"
+out="${PINN_OUT:-$here/../libpinn_b200.so}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 ${PINN_EXTRA_FLAGS:-}
        -Xcompiler -fPIC -Xptxas -v --threads 4)

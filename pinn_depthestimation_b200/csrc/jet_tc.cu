@@ -5,27 +5,35 @@
 // flat weight gradient.  Here the 256x256 hidden layers -- >99 % of the FLOPs -- run on the 5th-gen
 // tensor cores:
 //
-//   tile            32 points x 4 jet rows = 128 rows (row m = 4*point + jet)  -> UMMA M = 128
+//   tile            32 points x 4 jet rows = 128 rows                          -> UMMA M = 128
 //   forward  l      D[128 x 256] = A[128 x 256] * W_l^T          A: smem (K-major), B: W image via TMA
 //   adjoint  l      D[128 x 256] = Zbar[128 x 256] * W_l         A: smem (K-major), B: W^T image via TMA
 //   weight grad l   D[256 x 256] = Zbar^T * A_in  (two M=128 halves, K = 128 rows)
-//                                                                A, B: row-transposed images via TMA (K-major)
+//                                              A, B: MN-major (SWIZZLE_128B_BASE32B) images via TMA
 //   accumulators live in TMEM (512 columns), read back with tcgen05.ld for the tanh / jet / adjoint
 //   epilogues; the d->256 and 256->o edge layers (<1 % of the work) stay on the FP32 pipes.
 //
-// Warp roles (320 threads, one CTA per SM, persistent over tiles):
-//   warps 0-7  workers: edge layers, epilogues (TMEM -> registers -> operand image in smem / slab / RED)
-//   warp  8    producer: 1-D TMA bulk copies of weight images and slab chunks into a 4-stage ring
-//   warp  9    MMA issuer: one thread issues tcgen05.mma and tcgen05.commit; owns the TMEM allocation
+// Row order inside a tile: row m = 32*sp + 8*j + pp holds jet j of point 8*sp + pp (sp = TMEM
+// subpartition).  A tcgen05.ld.16x256b hands thread T of a warp the rows pp = T/4 and pp + 8 and two
+// adjacent columns, so two loads (lanes 0-15, 16-31) give ONE thread all four jets of a point for its
+// features: the tanh' coupling between the value and the tangent rows is thread-local (no shuffles) and
+// tanh is evaluated once per (point, feature).
 //
-// Operand image in shared memory ("interleaved", no swizzle): element (row m, feature f) at byte
-//   (f/4)*OP_LBO + m*16 + (f%4)*4, OP_LBO = 128*16 + 16: the canonical K-major UMMA layout with
-//   LBO = OP_LBO, SBO = 128; the 16-byte pad makes both thread-per-row and thread-per-feature accesses
-//   bank-conflict free.  kind::tf32 returns zeros for MN-major (transposed) operands on this part
-//   (tools/umma_probe.cu), so the weight-gradient contraction over ROWS takes both operands from
-//   row-transposed images in global memory ("T-image": (m, f) at float (m/16)*4096 + ((m%16)/4)*1024 +
-//   f*4 + m%4, i.e. 16-row chunks that are K-major with K = row): the activation slab is stored that way
-//   in the forward pass and Zbar is spilled that way in the reverse pass, 128 KB each per layer.
+// Warp roles (576 threads, one CTA per SM, persistent over tiles):
+//   warps 0-15 workers: edge layers, epilogues (TMEM -> registers -> operand image in smem / spill / RED)
+//   warp  16   producer: 1-D TMA bulk copies of weight images and spill chunks into a 4-stage ring
+//   warp  17   MMA issuer: one thread issues tcgen05.mma and tcgen05.commit; owns the TMEM allocation
+//
+// Operand image in shared memory (K-major, no swizzle): element (row m, feature f) at byte
+//   (f/4)*OP_LBO + m*16 + (f%4)*4, OP_LBO = 128*16 + 64: the canonical K-major UMMA layout with
+//   LBO = OP_LBO, SBO = 128; the 64-byte pad makes the 8-byte jets-in-thread accesses conflict-free.
+// Spill image in global memory ("P-image", 128 KB per layer per tile): 16-row chunks of 16 KB, each
+//   [8 panels of 32 features][16 rows][128 B] with the 32-byte units of a row XOR-swizzled by (row % 4):
+//   exactly the MN-major SWIZZLE_128B_BASE32B shared-memory layout (LBO 2048 between panels, SBO 512
+//   between 4-row atoms), the only MN-major layout kind::tf32 accepts (tools/umma_mn_probe.cu).  It is
+//   row-major per panel, so the epilogue threads write it straight from registers in full 32-byte sectors
+//   and read it back the same way in the reverse sweep; one image serves the adjoint epilogue AND, streamed
+//   back by TMA, the weight-gradient contraction over rows -- no transposition pass anywhere.
 #include "common.cuh"
 #include "residual.cuh"
 
@@ -34,23 +42,21 @@ namespace pinn {
 constexpr int TC_H = 256;                  // hidden width handled by this kernel
 constexpr int TC_M = 128;                  // rows per tile
 constexpr int TC_TP = 32;                  // points per tile
-#ifndef PINN_TC_WPS
-#define PINN_TC_WPS 4
-#endif
-constexpr int TC_WPS = PINN_TC_WPS;         // worker warps per TMEM subpartition (2 or 4)
+constexpr int TC_WPS = 4;                  // worker warps per TMEM subpartition
 constexpr int TC_WORKERS = 128 * TC_WPS;
 constexpr int TC_THREADS = TC_WORKERS + 64;
 constexpr int TC_WCOLS = TC_H / TC_WPS;    // columns of a 128x256 accumulator owned by one worker warp
-constexpr int TC_WBLK = TC_WCOLS / 16;     // 16-column blocks per worker
+constexpr int TC_NBLK = TC_WCOLS / 16;     // 16-column blocks per worker warp
 constexpr int TC_PARTS = TC_WORKERS / TC_H;  // worker threads per feature in the thread-per-feature phases
 constexpr int TC_STAGES = 4;
 constexpr int TC_STAGE_BYTES = 16384;
 constexpr int TC_STAGE_FLOATS = TC_STAGE_BYTES / 4;
-constexpr int OP_LBO = TC_M * 16 + 16;     // 2064
+constexpr int OP_LBO = TC_M * 16 + 64;     // 2112
 constexpr int OP_BYTES = (TC_H / 4) * OP_LBO;
+constexpr int TC_IMG = TC_M * TC_H;        // floats per spill image
+constexpr int TC_ZBUFS = 3;                // Zbar spill images in flight (layer l uses buffer l % 3)
 constexpr int TC_WCHUNKS = TC_H * TC_H * 4 / TC_STAGE_BYTES;   // 16 chunks per weight image
-constexpr int TC_SCHUNKS = TC_M * TC_H * 4 / TC_STAGE_BYTES;   // 8 chunks per slab entry
-constexpr int TC_MAX_HH = 7;               // hidden->hidden layers whose biases are staged in shared memory
+constexpr int TC_MAX_HH = 7;               // hidden->hidden layers whose bias gradients are staged in shared memory
 
 struct TcArgs {
   const float* params;
@@ -62,7 +68,7 @@ struct TcArgs {
   double* sums;
   float* out;
   float* dout[PINN_MAX_DIRS];
-  float* slab;            // per CTA: (L-2) T-images of layer outputs, then one T-image of Zbar
+  float* slab;            // per CTA: (L-2) P-images of layer outputs, then TC_ZBUFS P-images of Zbar
   long long slab_stride;  // floats per CTA
   long long n_points;
   int n_tiles;
@@ -169,12 +175,36 @@ __device__ __forceinline__ float warp_sum_tc(float v) {
   return v;
 }
 
-struct RowMajorJets {  // output jets of one point in the [128 rows][8] area, row = 4*p + j
+// 16 TMEM lanes x 16 columns, no wait: thread T gets, for u = 0..1:
+//   r[4u], r[4u+1] = (lane T/4, cols 8u + 2(T%4) + {0,1}),   r[4u+2], r[4u+3] = (lane T/4 + 8, same cols)
+__device__ __forceinline__ void tmem_ld_16x256b_x2_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// MN-major operand descriptor, SWIZZLE_128B_BASE32B (layout type 1): LBO = stride between 32-element
+// panels along M/N, SBO = stride between 4-row atoms along K
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return umma_desc(smem_addr, lbo_bytes, sbo_bytes) | ((uint64_t)1 << 61);
+}
+__device__ __forceinline__ void st_global_v2(float* p, float a, float b) {
+  asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ float2 ld_global_v2(const float* p) {
+  float2 v;
+  asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+  return v;
+}
+
+struct TileJets {  // output jets of one point in the [128 rows][8] area, row = 32*(p/8) + 8*j + p%8
   float* outs;
   int p;
-  __device__ __forceinline__ float get(int col, int j) const { return outs[(4 * p + j) * 8 + col]; }
-  __device__ __forceinline__ void set(int col, int j, float v) { outs[(4 * p + j) * 8 + col] = v; }
-  __device__ __forceinline__ void add(int col, int j, float v) { outs[(4 * p + j) * 8 + col] += v; }
+  __device__ __forceinline__ int row(int j) const { return 32 * (p >> 3) + 8 * j + (p & 7); }
+  __device__ __forceinline__ float get(int col, int j) const { return outs[row(j) * 8 + col]; }
+  __device__ __forceinline__ void set(int col, int j, float v) { outs[row(j) * 8 + col] = v; }
+  __device__ __forceinline__ void add(int col, int j, float v) { outs[row(j) * 8 + col] += v; }
 };
 
 #ifdef PINN_TC_DEBUG
@@ -188,15 +218,15 @@ struct RowMajorJets {  // output jets of one point in the [128 rows][8] area, ro
 template <bool BWD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     jet_tc_kernel(const __grid_constant__ pinn_desc_t D, const __grid_constant__ TcArgs A) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* op = smem_raw;                                   // operand image (A or Zbar)
   unsigned char* ring = op + OP_BYTES;
   float* w0s = reinterpret_cast<float*>(ring + TC_STAGES * TC_STAGE_BYTES);  // [H][8]  W0[f][c]
   float* wls = w0s + TC_H * 8;                                    // [8][H]  Wlast[c][f]
   float* outs = wls + 8 * TC_H;                                   // [128][8] output jets / seeds
   float* xin = outs + TC_M * 8;                                   // [32][8]
-  float* bias_s = xin + TC_TP * 8;                                // [TC_MAX_HH][H] hidden-layer biases
-  double* red = reinterpret_cast<double*>(bias_s + TC_MAX_HH * TC_H);  // [16]
+  float* db_s = xin + TC_TP * 8;                                  // [TC_MAX_HH][H] hidden-layer bias gradients
+  double* red = reinterpret_cast<double*>(db_s + TC_MAX_HH * TC_H);  // [16]
   uint64_t* full = reinterpret_cast<uint64_t*>(red + PINN_NSUMS);  // [S]
   uint64_t* empty = full + TC_STAGES;                             // [S]
   uint64_t* op_ready = empty + TC_STAGES;
@@ -214,9 +244,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const int NHH = L - 2;                      // hidden->hidden layers (tensor-core jobs per direction)
   const int kind = D.residual_kind;
   const int my_tiles = (A.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  float* slab = A.slab + (long long)blockIdx.x * A.slab_stride;
-  float* slab_r = slab + (size_t)(L - 2) * TC_M * TC_H;      // thread-private row images (reverse loads)
-  float* zt = slab_r + (size_t)(L - 2) * TC_M * TC_H;        // two T-images of Zbar (layer parity), split by feature half
+  float* slab = A.slab + (long long)blockIdx.x * A.slab_stride;  // P-images of a_0 .. a_{L-3}
+  float* zimg = slab + (size_t)(L - 2) * TC_IMG;                 // TC_ZBUFS P-images of Zbar
   const long long P0 = (long long)d * TC_H + TC_H;               // params of layer 0
   const long long PH = (long long)TC_H * TC_H + TC_H;            // params of a hidden->hidden layer
   const long long poffL = P0 + (long long)NHH * PH;              // params offset of the last layer
@@ -244,10 +273,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int c = i / TC_H, f = i - c * TC_H;
     wls[i] = c < o ? A.params[poffL + (long long)c * TC_H + f] : 0.f;
   }
-  for (int i = tid; i < TC_MAX_HH * TC_H; i += TC_THREADS) {
-    const int hl = i / TC_H, f = i - hl * TC_H;
-    bias_s[i] = hl < NHH ? A.params[P0 + (long long)hl * PH + (long long)TC_H * TC_H + f] : 0.f;
-  }
+  for (int i = tid; i < TC_MAX_HH * TC_H; i += TC_THREADS) db_s[i] = 0.f;
   if (warp == TC_WORKERS / 32 + 1) {
     tmem_alloc(tmem_ptr, 512);
     tmem_relinquish();
@@ -268,19 +294,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         tma_load_1d(ring + s * TC_STAGE_BYTES, src, TC_STAGE_BYTES, &full[s]);
         ++pc;
       };
+      auto load2 = [&](const float* src0, const float* src1) {   // two 8 KB pieces into one stage
+        const int s = pc % TC_STAGES;
+        mbar_wait(&empty[s], (uint32_t)(((pc / TC_STAGES) & 1) ^ 1));
+        mbar_expect_tx(&full[s], TC_STAGE_BYTES);
+        tma_load_1d(ring + s * TC_STAGE_BYTES, src0, TC_STAGE_BYTES / 2, &full[s]);
+        tma_load_1d(ring + s * TC_STAGE_BYTES + TC_STAGE_BYTES / 2, src1, TC_STAGE_BYTES / 2, &full[s]);
+        ++pc;
+      };
       for (int it = 0; it < my_tiles; ++it) {
         for (int hl = 0; hl < NHH; ++hl)
           for (int c = 0; c < TC_WCHUNKS; ++c)
             load(A.packed + (size_t)hl * 2 * TC_H * TC_H + (size_t)c * TC_STAGE_FLOATS);
         if (BWD) {
-          mbar_wait(slab_ready, (uint32_t)(it & 1));  // this tile's slab entries are written and fenced
+          mbar_wait(slab_ready, (uint32_t)(it & 1));  // this tile's activation spills are written and fenced
           // one weight-gradient half job = 128 Zbar features x 256 A_in features over the tile's 128 rows:
-          // per 32 rows one stage of Zbar^T (two 16-row half-chunks) and two stages of A_in^T
+          // per 32 rows one stage holding the half-h panels (8 KB) of two 16-row Zbar chunks, and two stages
+          // holding the two 16-row chunks of A_in
           auto load_dw_half = [&](int l, int h) {
-            const float* zsrc = zt + (size_t)(l & 1) * TC_M * TC_H + (size_t)h * (TC_M * TC_H / 2);
-            const float* asrc = slab + (size_t)(l - 1) * TC_M * TC_H;
+            const float* zsrc = zimg + (size_t)(l % TC_ZBUFS) * TC_IMG + (size_t)h * (TC_STAGE_FLOATS / 2);
+            const float* asrc = slab + (size_t)(l - 1) * TC_IMG;
             for (int g = 0; g < 4; ++g) {
-              load(zsrc + (size_t)g * TC_STAGE_FLOATS);
+              load2(zsrc + (size_t)(2 * g) * TC_STAGE_FLOATS, zsrc + (size_t)(2 * g + 1) * TC_STAGE_FLOATS);
               load(asrc + (size_t)(2 * g) * TC_STAGE_FLOATS);
               load(asrc + (size_t)(2 * g + 1) * TC_STAGE_FLOATS);
             }
@@ -290,7 +325,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               load(A.packed + (size_t)(l - 1) * 2 * TC_H * TC_H + (size_t)TC_H * TC_H +
                    (size_t)c * TC_STAGE_FLOATS);
             if (l < L - 2) load_dw_half(l + 1, 1);
-            mbar_wait(zt_ready, (uint32_t)(nzt & 1));  // Zbar_l has been spilled as a T-image
+            mbar_wait(zt_ready, (uint32_t)(nzt & 1));  // Zbar_l has been spilled
             ++nzt;
             load_dw_half(l, 0);
           }
@@ -302,6 +337,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // =========================================== MMA issuer =========================================
     if (lane == 0) {
       constexpr uint32_t idesc_k = umma_idesc(TC_M, TC_H, 0, 0);
+      constexpr uint32_t idesc_mn = umma_idesc(TC_M, TC_H, 1, 1);
       const uint32_t op_addr = smem_u32(op);
       const uint32_t ring_addr = smem_u32(ring);
       int cc = 0, jobs = 0, nB = 0;
@@ -335,7 +371,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           gemm_k();
         }
         if (BWD) {
-          // weight-gradient half job into TMEM columns 256..511: both operands are K-major with K = row
+          // weight-gradient half job into TMEM columns 256..511: both operands MN-major (contraction over rows)
           auto dw_half = [&]() {
             if (nB > 0) {
               mbar_wait(rb_free, (uint32_t)((nB - 1) & 1));   // the previous half has been drained
@@ -353,12 +389,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
                 for (int kk = 0; kk < 2; ++kk) {
                   const int kstep = g * 4 + i * 2 + kk;   // 8 rows per MMA
-                  const uint64_t ad = umma_desc(ring_addr + (uint32_t)sz * TC_STAGE_BYTES + (uint32_t)i * 8192u +
-                                                    (uint32_t)kk * 2u * (128u * 16u),
-                                                128 * 16, 128);
-                  const uint64_t bd = umma_desc(ring_addr + (uint32_t)sa * TC_STAGE_BYTES + (uint32_t)kk * 2u * (TC_H * 16),
-                                                TC_H * 16, 128);
-                  umma_tf32(tmem_base + 256u, ad, bd, idesc_k, kstep > 0 ? 1u : 0u);
+                  const uint64_t ad = umma_desc_mn(ring_addr + (uint32_t)sz * TC_STAGE_BYTES + (uint32_t)i * 8192u +
+                                                       (uint32_t)kk * 1024u,
+                                                   2048, 512);
+                  const uint64_t bd = umma_desc_mn(ring_addr + (uint32_t)sa * TC_STAGE_BYTES + (uint32_t)kk * 1024u,
+                                                   2048, 512);
+                  umma_tf32(tmem_base + 256u, ad, bd, idesc_mn, kstep > 0 ? 1u : 0u);
                 }
                 umma_commit(&empty[sa]);
               }
@@ -381,11 +417,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // =========================================== workers ============================================
     const int sp = warp & 3, half = warp >> 2;   // `half` = which TC_WCOLS-wide column slice this warp owns
     const int cbase = half * TC_WCOLS;
-    const int m = sp * 32 + lane;          // this thread's row of the tile = its TMEM lane
-    const int p = m >> 2, j = m & 3;
-    const int leader = lane & ~3;
-    const uint32_t tmem_row = tmem_base + ((uint32_t)(sp * 32) << 16);
+    const int pp = lane >> 2, cq = lane & 3;     // point within the subpartition, column pair within 8 columns
+    const int pt = sp * 8 + pp;                  // this thread's point of the tile
+    const int mrow0 = sp * 32 + pp;              // row of its value jet; jet j sits at row mrow0 + 8 j
+    const uint32_t tmem_sp = tmem_base + ((uint32_t)(sp * 32) << 16);
     const float inv_cnt = (kind == PINN_RES_CONT_ONLY && A.mask_count) ? 1.0f / *A.mask_count : 0.f;
+    // this thread's features in block b (16 columns): f = cbase + 16 b + 8 u + 2 cq + e, u, e in {0, 1}
+    // operand image: element (jet j, block b, u, e) at op_thr + ((cbase + 16 b)/4 + 2u) * OP_LBO + j * 128 + e * 4
+    unsigned char* op_thr = op + (cbase / 4 + (cq >> 1)) * OP_LBO + mrow0 * 16 + (cq & 1) * 8;
+    // P-image: element (j, b, u, e) at float  img_thr + (j>>1)*4096 + (j&1)*256 + (b>>1)*512 + ((2(b&1)+u) ^ (pp&3))*8 + e
+    const int img_thr = (2 * sp) * TC_STAGE_FLOATS + (2 * half) * 512 + pp * 32 + cq * 2;
+    auto img_off = [&](int j, int b, int u) {
+      return img_thr + (j >> 1) * TC_STAGE_FLOATS + (j & 1) * 256 + (b >> 1) * 512 + (((2 * (b & 1) + u) ^ (pp & 3)) << 3);
+    };
     int mj = 0;   // adjoint / forward MMA jobs waited for
     int nbw = 0;  // weight-gradient half jobs drained
     TCT_DECL
@@ -399,147 +443,176 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       fence_async_proxy();
       mbar_arrive(op_ready);
     };
-    // 16 consecutive features f0.. of row m -> operand image (and slab entry e)
-    auto store_op = [&](int f0, const float (&v)[16]) {
+    // all four jets of this thread's point for the 4 features of block b: v[j][2u+e]
+    auto ld_block = [&](int b, float (&v)[4][4]) {
+      uint32_t ra[8], rb[8];
+      const uint32_t col = (uint32_t)(cbase + 16 * b);
+      tmem_ld_16x256b_x2_nowait(tmem_sp + col, ra);
+      tmem_ld_16x256b_x2_nowait(tmem_sp + (16u << 16) + col, rb);
+      tmem_wait_ld();
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        *reinterpret_cast<float4*>(op + (f0 / 4 + q) * OP_LBO + m * 16) =
-            make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          v[0][2 * u + e] = __uint_as_float(ra[4 * u + e]);
+          v[1][2 * u + e] = __uint_as_float(ra[4 * u + 2 + e]);
+          v[2][2 * u + e] = __uint_as_float(rb[4 * u + e]);
+          v[3][2 * u + e] = __uint_as_float(rb[4 * u + 2 + e]);
+        }
     };
-    // T-image (row-transposed, 16-row chunks): (row m, feature f) at float (m/16)*4096 + ((m%16)/4)*1024 + f*4 + m%4.
-    // Each warp transposes the 32 rows x 128 features it owns out of the operand image: 4 conflict-free
-    // LDS.32 (the 4 rows of a quad) -> one coalesced 16-byte store per feature.
-    auto t_copy = [&](float* img, bool split) {
-      __syncwarp();
-#pragma unroll 4
-      for (int itc = 0; itc < TC_WCOLS / 4; ++itc) {
-        const int idx = itc * 32 + lane;
-        const int q = idx / TC_WCOLS, f = cbase + (idx % TC_WCOLS);
-        const unsigned char* src = op + (f >> 2) * OP_LBO + (sp * 32 + 4 * q) * 16 + (f & 3) * 4;
-        float4 v;
-        v.x = *reinterpret_cast<const float*>(src);
-        v.y = *reinterpret_cast<const float*>(src + 16);
-        v.z = *reinterpret_cast<const float*>(src + 32);
-        v.w = *reinterpret_cast<const float*>(src + 48);
-        const size_t dst = split ? (size_t)(f >> 7) * (TC_M * TC_H / 2) + (size_t)(2 * sp + (q >> 2)) * (TC_STAGE_FLOATS / 2) +
-                                       (size_t)(q & 3) * (TC_H * 2) + (size_t)(f & 127) * 4
-                                 : (size_t)(2 * sp + (q >> 2)) * TC_STAGE_FLOATS + (size_t)(q & 3) * (TC_H * 4) + (size_t)f * 4;
-        *reinterpret_cast<float4*>(img + dst) = v;
+    auto st_op_block = [&](int b, const float (&v)[4][4]) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float2*>(op_thr + (4 * b + 2 * u) * OP_LBO + j * 128) = make_float2(v[j][2 * u], v[j][2 * u + 1]);
+    };
+    auto ld_op_block = [&](int b, float (&v)[4][4]) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 t = *reinterpret_cast<const float2*>(op_thr + (4 * b + 2 * u) * OP_LBO + j * 128);
+          v[j][2 * u] = t.x, v[j][2 * u + 1] = t.y;
+        }
+    };
+    auto st_img_block = [&](float* img, int b, const float (&v)[4][4]) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) st_global_v2(img + img_off(j, b, u), v[j][2 * u], v[j][2 * u + 1]);
+    };
+    auto ld_img_block = [&](const float* img, int b, float (&v)[4][4]) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 t = ld_global_v2(img + img_off(j, b, u));
+          v[j][2 * u] = t.x, v[j][2 * u + 1] = t.y;
+        }
+    };
+    // forward activation: pre-activation jets z (value row already carries the bias) -> post-activation jets
+    auto activate = [&](float (&z)[4][4]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float a = tanh_approx(z[0][i]);
+        const float s = fmaf(-a, a, 1.f);
+        z[0][i] = round_tf32(a);
+        z[1][i] = round_tf32(s * z[1][i]);
+        z[2][i] = round_tf32(s * z[2][i]);
+        z[3][i] = round_tf32(s * z[3][i]);
       }
     };
-    // R-image: thread-private float4 slots [(block b, q)][worker thread] (coalesced), for the reverse loads;
-    // written as a copy of this thread's own row out of the operand image, after the MMA has been released
-    const int wtid = tid;  // workers are threads 0..255
-    auto r_copy = [&](float* img) {
-#pragma unroll 8
-      for (int c = 0; c < TC_WCOLS / 4; ++c)
-        reinterpret_cast<float4*>(img)[(size_t)c * TC_WORKERS + wtid] =
-            *reinterpret_cast<const float4*>(op + (cbase / 4 + c) * OP_LBO + m * 16);
-    };
-    auto r_load = [&](const float* img, int b, float (&v)[16]) {
+    // adjoint through the activation: ab = adjoint of the post-activation jets, act = stored post-activation
+    // jets -> ab = adjoint of the pre-activation jets (Zbar)
+    auto adjoint = [&](float (&ab)[4][4], const float (&act)[4][4]) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 t = reinterpret_cast<const float4*>(img)[(size_t)(b * 4 + q) * TC_WORKERS + wtid];
-        v[4 * q] = t.x, v[4 * q + 1] = t.y, v[4 * q + 2] = t.z, v[4 * q + 3] = t.w;
+      for (int i = 0; i < 4; ++i) {
+        const float a = act[0][i];
+        const float s = fmaf(-a, a, 1.f);
+        const float pr = fmaf(ab[1][i], act[1][i], fmaf(ab[2][i], act[2][i], ab[3][i] * act[3][i]));
+        ab[0][i] = round_tf32(fmaf(-2.f * a, pr, ab[0][i] * s));
+        ab[1][i] = round_tf32(ab[1][i] * s);
+        ab[2][i] = round_tf32(ab[2][i] * s);
+        ab[3][i] = round_tf32(ab[3][i] * s);
       }
     };
-    // forward activation on 16 features: z (pre-activation of this row) -> post-activation jets
-    auto activate = [&](float (&z)[16], const float* bias) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float a = tanh_approx(z[i] + (bias ? bias[i] : 0.f));
-        const float al = __shfl_sync(0xffffffffu, a, leader);
-        z[i] = round_tf32(j == 0 ? a : (1.f - al * al) * z[i]);
-      }
-    };
-    // adjoint through the activation: abar (adjoint of post-activation jets of this row), act (stored
-    // post-activation jets of this row) -> adjoint of the pre-activation jets
-    auto adjoint = [&](float (&ab)[16], const float (&act)[16]) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float al = __shfl_sync(0xffffffffu, act[i], leader);
-        const float s = 1.f - al * al;
-        float pr = j == 0 ? 0.f : ab[i] * act[i];
-        pr += __shfl_xor_sync(0xffffffffu, pr, 1);
-        pr += __shfl_xor_sync(0xffffffffu, pr, 2);
-        ab[i] = round_tf32(j == 0 ? fmaf(-2.f * al, pr, ab[i] * s) : ab[i] * s);
-      }
+    // bias gradient of a hidden layer: sum over the tile's points of the value-row Zbar.  The 8 points of a
+    // warp sit in lanes 4 pp + cq: halving butterfly over lane bits 4, 3, 2, then one shared-memory atomic
+    // per feature (16 lanes), accumulated over all tiles and flushed once at kernel exit.
+    auto db_block = [&](float* dbl, int b, const float (&zb)[4]) {
+      const bool b4 = lane & 16, b3 = lane & 8;
+      float k0 = b4 ? zb[2] : zb[0], k1 = b4 ? zb[3] : zb[1];
+      const float s0 = b4 ? zb[0] : zb[2], s1 = b4 ? zb[1] : zb[3];
+      k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+      k1 += __shfl_xor_sync(0xffffffffu, s1, 16);   // holds u = b4, e = 0 / 1
+      float k = b3 ? k1 : k0;
+      const float s = b3 ? k0 : k1;
+      k += __shfl_xor_sync(0xffffffffu, s, 8);      // holds u = b4, e = b3
+      k += __shfl_xor_sync(0xffffffffu, k, 4);
+      if (!(lane & 4)) atomicAdd(dbl + cbase + 16 * b + 8 * (b4 ? 1 : 0) + 2 * cq + (b3 ? 1 : 0), k);
     };
 
     for (int it = 0; it < my_tiles; ++it) {
       const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
       const long long p0 = tile * TC_TP;
       for (int i = tid; i < TC_TP * 8; i += TC_WORKERS) {
-        const int pp = i >> 3, c = i & 7;
-        const long long gp = p0 + pp;
+        const int pq = i >> 3, c = i & 7;
+        const long long gp = p0 + pq;
         xin[i] = (c < d && gp < A.n_points) ? A.inputs[gp * d + c] : 0.f;
       }
       worker_bar();
       TCT(0)
       // ---------------- layer 0 (d -> 256) on the FP32 pipes ----------------
       {
-        const int dircol = (j >= 1 && j - 1 < D.n_dirs) ? D.dir_cols[j - 1] : -1;
-        for (int b = 0; b < TC_WBLK; ++b) {
-          const int f0 = cbase + b * 16;
-          float z[16];
+        float x[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float* wr = w0s + (f0 + i) * 8;
-            float acc;
-            if (j == 0) {
-              acc = A.params[(long long)d * TC_H + f0 + i];
-              for (int c = 0; c < d; ++c) acc = fmaf(xin[p * 8 + c], wr[c], acc);
-            } else {
-              acc = dircol >= 0 ? wr[dircol] : 0.f;
+        for (int c = 0; c < 8; ++c) x[c] = xin[pt * 8 + c];
+        const float* b0 = A.params + (long long)d * TC_H;
+        for (int b = 0; b < TC_NBLK; ++b) {
+          float z[4][4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int f = cbase + 16 * b + 8 * (i >> 1) + 2 * cq + (i & 1);
+            const float4 wa = *reinterpret_cast<const float4*>(w0s + f * 8);
+            const float4 wb = *reinterpret_cast<const float4*>(w0s + f * 8 + 4);
+            const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+            float acc = __ldg(b0 + f);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc = fmaf(x[c], w[c], acc);
+            z[0][i] = acc;
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj) {
+              float t = 0.f;
+              if (jj < D.n_dirs) {
+                const int dc = D.dir_cols[jj];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) t = (c == dc) ? w[c] : t;
+              }
+              z[1 + jj][i] = t;
             }
-            z[i] = acc;
           }
-          activate(z, nullptr);
-          store_op(f0, z);
+          activate(z);
+          st_op_block(b, z);
+          if (BWD && NHH >= 1) st_img_block(slab, b, z);
         }
       }
       TCT(1)
       signal_ready();
-      if (BWD && NHH >= 1) {
-        r_copy(slab_r);
-        t_copy(slab, false);
-      }
-      TCT(3)
       // ---------------- hidden layers 1..L-2 on the tensor cores ----------------
       for (int l = 1; l <= L - 2; ++l) {
+        const float* bias_l = A.params + P0 + (long long)(l - 1) * PH + (long long)TC_H * TC_H + cbase + 2 * cq;
+        float bl[TC_NBLK][4];
+#pragma unroll
+        for (int b = 0; b < TC_NBLK; ++b)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) bl[b][i] = __ldg(bias_l + 16 * b + 8 * (i >> 1) + (i & 1));
         wait_mma();
         TCT(2)
-        const float* bias_l = (l - 1 < TC_MAX_HH) ? bias_s + (l - 1) * TC_H
-                                                  : A.params + P0 + (long long)(l - 1) * PH + (long long)TC_H * TC_H;
-        for (int b = 0; b < TC_WBLK; ++b) {
-          const int f0 = cbase + b * 16;
-          float z[16];
-          tmem_ld16(tmem_row + (uint32_t)f0, z);
-          // value rows: a = tanh(z + b); tangent rows: s * zdot with s = 1 - a^2 of the point's value row
+        float* img = slab + (size_t)l * TC_IMG;
+        const bool spill = BWD && l <= L - 3;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float a = tanh_approx(z[i] + bias_l[f0 + i]);
-            const float al = __shfl_sync(0xffffffffu, a, leader);
-            z[i] = round_tf32(j == 0 ? a : (1.f - al * al) * z[i]);
-          }
-          store_op(f0, z);
+        for (int b = 0; b < TC_NBLK; ++b) {
+          float z[4][4];
+          ld_block(b, z);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) z[0][i] += bl[b][i];
+          activate(z);
+          st_op_block(b, z);
+          if (spill) st_img_block(img, b, z);
         }
         TCT(1)
         if (l < L - 2) signal_ready();
-        if (BWD && l <= L - 3) {
-          r_copy(slab_r + (size_t)l * TC_M * TC_H);
-          t_copy(slab + (size_t)l * TC_M * TC_H, false);
-        }
-        TCT(3)
       }
       if (BWD) {
-        // the TMA engine reads the slab at L2: publish the generic-proxy stores at GPU scope first
+        // the TMA engine reads the spills at L2: publish the generic-proxy stores at GPU scope first
         __threadfence();
         fence_async_proxy();
         mbar_arrive(slab_ready);
       }
       tc_fence_before();
       worker_bar();
+      TCT(3)
       // ---------------- last layer (256 -> o) on the FP32 pipes ----------------
       {
         constexpr int NCS = TC_WORKERS / 128, NCI = 8 / NCS;
@@ -559,7 +632,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int ci = 0; ci < NCI; ++ci) {
           const int c = cs + NCS * ci;
           float v = acc[ci];
-          if ((mm & 3) == 0 && c < o) v += A.params[poffL + (long long)TC_H * o + c];
+          if (((mm >> 3) & 3) == 0 && c < o) v += A.params[poffL + (long long)TC_H * o + c];
           outs[mm * 8 + c] = c < o ? v : 0.f;
         }
       }
@@ -567,7 +640,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       // ---------------- residual / misfit epilogue: warp 0, one lane per point ----------------
       if (warp == 0) {
         const long long gp = p0 + lane;
-        RowMajorJets acc{outs, lane};
+        TileJets acc{outs, lane};
         float ls[PINN_NSUMS];
         residual_epilogue<4>(D, acc, true, gp < A.n_points, gp, xin + lane * 8,
                              EpiArgs{A.targets, nullptr, {nullptr, nullptr, nullptr}, A.out,
@@ -605,54 +678,57 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           if (c < o) atomicAdd(A.grad + poffL + (long long)c * TC_H + f, acc[c]);
         if (tid < o) {
           float s = 0.f;
-          for (int pp = 0; pp < TC_TP; ++pp) s += outs[(4 * pp) * 8 + tid];
+          for (int pq = 0; pq < TC_TP; ++pq) s += outs[(32 * (pq >> 3) + (pq & 7)) * 8 + tid];
           atomicAdd(A.grad + poffL + (long long)TC_H * o + tid, s);
         }
       }
       worker_bar();
       // ---- abar = zbar_last * W_last, through the activation of layer L-2 -> Zbar_{L-2} in place ----
       {
-        float zl[8];
+        float zl[4][8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) zl[c] = outs[m * 8 + c];
-        for (int b = 0; b < TC_WBLK; ++b) {
-          const int f0 = cbase + b * 16;
-          float ab[16], act[16];
+        for (int j = 0; j < 4; ++j) {
+          const float4 t0 = *reinterpret_cast<const float4*>(outs + (mrow0 + 8 * j) * 8);
+          const float4 t1 = *reinterpret_cast<const float4*>(outs + (mrow0 + 8 * j) * 8 + 4);
+          zl[j][0] = t0.x, zl[j][1] = t0.y, zl[j][2] = t0.z, zl[j][3] = t0.w;
+          zl[j][4] = t1.x, zl[j][5] = t1.y, zl[j][6] = t1.z, zl[j][7] = t1.w;
+        }
+        float* zdst = zimg + (size_t)((L - 2) % TC_ZBUFS) * TC_IMG;
+        float* dbl = db_s + (size_t)(L - 3) * TC_H;
+        for (int b = 0; b < TC_NBLK; ++b) {
+          float ab[4][4], act[4][4];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float a = 0.f;
+          for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int c = 0; c < 8; ++c) a = fmaf(zl[c], wls[c * TC_H + f0 + i], a);
-            ab[i] = a;
+            for (int i = 0; i < 4; ++i) ab[j][i] = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const float2 w = *reinterpret_cast<const float2*>(wls + c * TC_H + cbase + 16 * b + 8 * u + 2 * cq);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                ab[j][2 * u] = fmaf(zl[j][c], w.x, ab[j][2 * u]);
+                ab[j][2 * u + 1] = fmaf(zl[j][c], w.y, ab[j][2 * u + 1]);
+              }
+            }
           }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 v = *reinterpret_cast<const float4*>(op + (f0 / 4 + q) * OP_LBO + m * 16);
-            act[4 * q] = v.x, act[4 * q + 1] = v.y, act[4 * q + 2] = v.z, act[4 * q + 3] = v.w;
-          }
+          ld_op_block(b, act);
           adjoint(ab, act);
-          store_op(f0, ab);
+          st_op_block(b, ab);
+          st_img_block(zdst, b, ab);
+          if (L - 3 < TC_MAX_HH) db_block(dbl, b, ab[0]);
         }
       }
-      t_copy(zt + (size_t)((L - 2) & 1) * TC_M * TC_H, true);
       __threadfence();
       fence_async_proxy();
       mbar_arrive(zt_ready);
-      worker_bar();
+      signal_ready();                       // adjoint job of layer L-2 may start
       TCT(5)
       // ---- hidden layers L-2 .. 1, software-pipelined ----
       //   tensor core: adjoint job of layer l (TMEM columns 0..255), weight-gradient halves (columns 256..511)
-      //   workers:     adjoint epilogue of layer l | drain half 1 of layer l+1 | spill Zbar_{l-1}^T | drain half 0 of layer l
-      // The only serial chain is adjoint epilogue -> adjoint MMA -> adjoint epilogue; the drains hide behind it.
-      auto bias_grad = [&](int l) {   // sum over the value rows of Zbar_l (thread per feature)
-        const int f = tid & (TC_H - 1), part = tid / TC_H;
-        const unsigned char* zp = op + (f >> 2) * OP_LBO + (f & 3) * 4;
-        float sacc = 0.f;
-#pragma unroll 8
-        for (int pp = part * (TC_TP / TC_PARTS); pp < (part + 1) * (TC_TP / TC_PARTS); ++pp)
-          sacc += *reinterpret_cast<const float*>(zp + (4 * pp) * 16);
-        atomicAdd(A.grad + P0 + (long long)(l - 1) * PH + (long long)TC_H * TC_H + f, sacc);
-      };
+      //   workers:     adjoint epilogue of layer l (Zbar_{l-1} -> operand image + spill) | drain half 1 of layer
+      //                l+1 | drain half 0 of layer l
       // drain TMEM columns 256..511 = dW rows [128h, 128h+128) of layer l.  16x256b loads: the 4 lanes of a
       // quad hold 8 consecutive columns of one row, so every RED instruction updates full 32-byte sectors
       auto drain = [&](int l, int h) {
@@ -679,51 +755,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         tc_fence_before();
         mbar_arrive(rb_free);
       };
-      bias_grad(L - 2);
-      signal_ready();                       // adjoint job of layer L-2 may start
-      TCT(6)
       for (int l = L - 2; l >= 1; --l) {
-        // adjoint through the activation of layer l-1 -> Zbar_{l-1} in place
+        // adjoint through the activation of layer l-1 -> Zbar_{l-1} in place (+ spill for its weight gradient)
         {
-          const float* rimg = slab_r + (size_t)(l - 1) * TC_M * TC_H;
-          float act[16], nxt[16];
-          r_load(rimg, 0, act);   // issued before the wait: the loads overlap the adjoint MMA
+          const float* aimg = slab + (size_t)(l - 1) * TC_IMG;
+          float* zdst = zimg + (size_t)((l - 1) % TC_ZBUFS) * TC_IMG;
+          float* dbl = db_s + (size_t)(l >= 2 ? l - 2 : 0) * TC_H;
+          const bool hidden = l > 1;
+          float act[4][4], nxt[4][4];
+          ld_img_block(aimg, 0, act);   // issued before the wait: the loads overlap the adjoint MMA
           wait_mma();
           TCT(9)
-          for (int b = 0; b < TC_WBLK; ++b) {
-            const int f0 = cbase + b * 16;
-            float ab[16];
-            if (b < TC_WBLK - 1) r_load(rimg, b + 1, nxt);
-            tmem_ld16(tmem_row + (uint32_t)f0, ab);
-            adjoint(ab, act);
-            store_op(f0, ab);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) act[i] = nxt[i];
+          for (int b = 0; b < TC_NBLK; ++b) {
+            float ab[4][4];
+            if (b < TC_NBLK - 1) ld_img_block(aimg, b + 1, nxt);
+            ld_block(b, ab);
+            adjoint(ab, act);
+            st_op_block(b, ab);
+            if (hidden) {
+              st_img_block(zdst, b, ab);
+              if (l - 2 < TC_MAX_HH) db_block(dbl, b, ab[0]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) act[j][i] = nxt[j][i];
           }
         }
-        tc_fence_before();
-        worker_bar();                       // Zbar_{l-1} complete in the operand image
         TCT(10)
         if (l > 1) {
-          bias_grad(l - 1);
+          __threadfence();
+          fence_async_proxy();
+          mbar_arrive(zt_ready);
           signal_ready();                   // adjoint job of layer l-1 may start
         }
         TCT(6)
         if (l < L - 2) drain(l + 1, 1);
         TCT(8)
-        if (l > 1) {
-          // Zbar_{l-1}^T feeds the weight-gradient jobs of layer l-1.  Its buffer (layer parity) was last read
-          // by the half-1 job of layer l+1, which the drain above has just seen complete.
-          t_copy(zt + (size_t)((l - 1) & 1) * TC_M * TC_H, true);
-          __threadfence();
-          fence_async_proxy();
-          mbar_arrive(zt_ready);
-        }
-        TCT(11)
         drain(l, 0);
         TCT(7)
       }
       drain(1, 1);
+      tc_fence_before();
       worker_bar();
       TCT(8)
       // ---- layer 0: dW0[f][c], db0[f] from Zbar_0 (thread per feature) ----
@@ -733,13 +807,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         float acc[8], tj[3] = {0.f, 0.f, 0.f}, sb = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-        for (int pp = part * (TC_TP / TC_PARTS); pp < (part + 1) * (TC_TP / TC_PARTS); ++pp) {
-          const float z0 = *reinterpret_cast<const float*>(zp + (4 * pp) * 16);
+        for (int pq = part * (TC_TP / TC_PARTS); pq < (part + 1) * (TC_TP / TC_PARTS); ++pq) {
+          const int r0 = 32 * (pq >> 3) + (pq & 7);
+          const float z0 = *reinterpret_cast<const float*>(zp + r0 * 16);
           sb += z0;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) acc[c] = fmaf(z0, xin[pp * 8 + c], acc[c]);
+          for (int c = 0; c < 8; ++c) acc[c] = fmaf(z0, xin[pq * 8 + c], acc[c]);
 #pragma unroll
-          for (int jj = 0; jj < 3; ++jj) tj[jj] += *reinterpret_cast<const float*>(zp + (4 * pp + 1 + jj) * 16);
+          for (int jj = 0; jj < 3; ++jj) tj[jj] += *reinterpret_cast<const float*>(zp + (r0 + 8 * (1 + jj)) * 16);
         }
         for (int jj = 0; jj < D.n_dirs; ++jj) {
 #pragma unroll
@@ -754,13 +829,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       worker_bar();
       TCT(12)
     }
+    if (BWD) {
+      // bias gradients of the hidden layers, accumulated over all tiles of this CTA
+      worker_bar();
+      for (int i = tid; i < TC_MAX_HH * TC_H; i += TC_WORKERS) {
+        const int hl = i / TC_H, f = i - hl * TC_H;
+        if (hl < NHH) atomicAdd(A.grad + P0 + (long long)hl * PH + (long long)TC_H * TC_H + f, db_s[i]);
+      }
+    }
 #ifdef PINN_TC_DEBUG
     if (blockIdx.x == 0 && tid == 0) {
       long long tot = 0;
       for (int i = 0; i < 13; ++i) tot += tct[i];
-      printf("TC phases (cycles per tile, %d tiles): in+bar %lld | L0+fwd-epi %lld | fwd-wait-mma %lld | fwd signal+copies %lld | last+residual %lld | rev-last %lld | db+signal %lld | wait-dW %lld | drain %lld | signal+wait-adj %lld | adj-epi %lld | tcopy+fence+bar %lld | L0-rev %lld | total %lld\n", my_tiles,
+      printf("TC phases (cycles per tile, %d tiles): in+bar %lld | L0+fwd-epi %lld | fwd-wait-mma %lld | fence+bar %lld | last+residual %lld | rev-last %lld | fence+signal %lld | drain0 %lld | drain1 %lld | wait-adj %lld | adj-epi %lld | L0-rev %lld | total %lld\n", my_tiles,
              tct[0] / my_tiles, tct[1] / my_tiles, tct[2] / my_tiles, tct[3] / my_tiles, tct[4] / my_tiles, tct[5] / my_tiles, tct[6] / my_tiles,
-             tct[7] / my_tiles, tct[8] / my_tiles, tct[9] / my_tiles, tct[10] / my_tiles, tct[11] / my_tiles, tct[12] / my_tiles, tot / my_tiles);
+             tct[7] / my_tiles, tct[8] / my_tiles, tct[9] / my_tiles, tct[10] / my_tiles, tct[12] / my_tiles, tot / my_tiles);
     }
 #endif
   }
@@ -821,7 +904,7 @@ int tc_workspace(const pinn_desc_t* D, long long n_points, int sms, size_t* pack
   if (g < 1) g = 1;
   *grid = (int)g;
   *packed_bytes = (size_t)(L - 2) * 2 * TC_H * TC_H * 4;
-  *slab_stride = (long long)(2 * (L - 2) + 2) * TC_M * TC_H;   // T- and R-images of (L-2) layer outputs + 2 Zbar spills
+  *slab_stride = (long long)((L - 2) + TC_ZBUFS) * TC_IMG;   // P-images of (L-2) layer outputs + the Zbar spills in flight
   *slab_bytes = (size_t)g * (size_t)(*slab_stride) * 4;
   return PINN_OK;
 }
