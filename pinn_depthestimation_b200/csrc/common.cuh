@@ -36,8 +36,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Parity wait with a watchdog: a protocol bug must fail the launch (trap -> CUDA error at the next sync) instead
+// of hanging the device.  2^26 failed polls is seconds of wall clock, far beyond any legitimate wait here.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
+  uint32_t done, spins = 0;
   do {
     asm volatile(
         "{\n"
@@ -48,6 +50,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+    if (!done && ++spins > (1u << 26)) {
+#ifdef PINN_TC_DEBUG
+      printf("pinn_b200: mbarrier wait timed out (block %d thread %d barrier@%u parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, smem_u32(bar), parity);
+#endif
+      __trap();
+    }
   } while (!done);
 }
 // 1-D bulk copy global -> shared; completion is counted in bytes on an mbarrier (SASS: UBLKCP).

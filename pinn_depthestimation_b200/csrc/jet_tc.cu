@@ -80,6 +80,7 @@ struct TcArgs {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_proxy_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TC_WORKERS) : "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -232,8 +233,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint64_t* op_ready = empty + TC_STAGES;
   uint64_t* mma_done = op_ready + 1;
   uint64_t* slab_ready = mma_done + 1;
-  uint64_t* zt_ready = slab_ready + 1;
-  uint64_t* mma_done_b = zt_ready + 1;   // weight-gradient accumulator (TMEM columns 256..511) complete
+  uint64_t* zt_ready = slab_ready + 1;   // [2], alternating per Zbar spill: the workers may run one spill ahead of the
+                                         // producer's wait, and a single parity-waited barrier must never advance twice unseen
+  uint64_t* mma_done_b = zt_ready + 2;   // weight-gradient accumulator (TMEM columns 256..511) complete
   uint64_t* rb_free = mma_done_b + 1;    // ... and drained by the workers
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(rb_free + 1);
 
@@ -259,7 +261,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     mbar_init(op_ready, TC_WORKERS);
     mbar_init(mma_done, 1);
     mbar_init(slab_ready, TC_WORKERS);
-    mbar_init(zt_ready, TC_WORKERS);
+    mbar_init(&zt_ready[0], TC_WORKERS);
+    mbar_init(&zt_ready[1], TC_WORKERS);
     mbar_init(mma_done_b, 1);
     mbar_init(rb_free, TC_WORKERS);
     mbar_fence_init();
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               load(A.packed + (size_t)(l - 1) * 2 * TC_H * TC_H + (size_t)TC_H * TC_H +
                    (size_t)c * TC_STAGE_FLOATS);
             if (l < L - 2) load_dw_half(l + 1, 1);
-            mbar_wait(zt_ready, (uint32_t)(nzt & 1));  // Zbar_l has been spilled
+            mbar_wait(&zt_ready[nzt & 1], (uint32_t)((nzt >> 1) & 1));  // Zbar_l has been spilled
             ++nzt;
             load_dw_half(l, 0);
           }
@@ -338,9 +341,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     if (lane == 0) {
       constexpr uint32_t idesc_k = umma_idesc(TC_M, TC_H, 0, 0);
       constexpr uint32_t idesc_mn = umma_idesc(TC_M, TC_H, 1, 1);
-      const uint32_t op_addr = smem_u32(op);
-      const uint32_t ring_addr = smem_u32(ring);
-      int cc = 0, jobs = 0, nB = 0;
+      // The issue loop runs on ONE thread: every scalar instruction in it is on the tensor pipe's critical path
+      // (a 128x256x8 TF32 MMA retires in ~130 cycles, tools/mma_rate_probe.cu).  Descriptors are therefore
+      // built once; per MMA only the 14-bit start-address field (16-byte units) advances by a compile-time
+      // constant.  Every job consumes a multiple of TC_STAGES ring stages, so stage indices are constants too.
+      static_assert(TC_WCHUNKS % TC_STAGES == 0 && 12 % TC_STAGES == 0, "jobs must keep the ring stage index aligned");
+      const uint64_t ad_op = umma_desc(smem_u32(op), OP_LBO, 128);            // + kstep * (2 * OP_LBO / 16)
+      const uint64_t bd_k = umma_desc(smem_u32(ring), TC_H * 16, 128);        // K-major weight chunk in stage 0
+      const uint64_t d_mn = umma_desc_mn(smem_u32(ring), 2048, 512);          // MN-major spill chunk in stage 0
+      constexpr uint64_t STG = TC_STAGE_BYTES / 16;
+      uint32_t rp = 0;      // parity of the ring pass (flips every TC_STAGES chunks)
+      int jobs = 0, nB = 0;
       auto wait_ready = [&]() {
         mbar_wait(op_ready, (uint32_t)(jobs & 1));
         ++jobs;
@@ -348,20 +359,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       };
       // D[128 x 256] = OP (K-major, 256 features) * image chunks (K-major)
       auto gemm_k = [&]() {
+#pragma unroll
         for (int c = 0; c < TC_WCHUNKS; ++c) {
-          const int s = cc % TC_STAGES;
-          mbar_wait(&full[s], (uint32_t)((cc / TC_STAGES) & 1));
-          tc_fence_after();
+          const int s = c % TC_STAGES;
+          mbar_wait(&full[s], rp);
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk) {
             const int kstep = c * 2 + kk;  // 8 contraction features per MMA = two 16-byte K chunks
-            const uint64_t ad = umma_desc(op_addr + (uint32_t)kstep * 2u * OP_LBO, OP_LBO, 128);
-            const uint64_t bd = umma_desc(ring_addr + (uint32_t)s * TC_STAGE_BYTES + (uint32_t)kk * 2u * (TC_H * 16),
-                                          TC_H * 16, 128);
-            umma_tf32(tmem_base, ad, bd, idesc_k, kstep > 0 ? 1u : 0u);
+            umma_tf32(tmem_base, ad_op + (uint64_t)(kstep * (2 * OP_LBO / 16)),
+                      bd_k + (uint64_t)s * STG + (uint64_t)(kk * (2 * TC_H * 16 / 16)), idesc_k, kstep > 0 ? 1u : 0u);
           }
           umma_commit(&empty[s]);
-          ++cc;
+          if (s == TC_STAGES - 1) rp ^= 1u;
         }
         umma_commit(mma_done);
       };
@@ -371,36 +380,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           gemm_k();
         }
         if (BWD) {
-          // weight-gradient half job into TMEM columns 256..511: both operands MN-major (contraction over rows)
+          // weight-gradient half job into TMEM columns 256..511: both operands MN-major (contraction over rows);
+          // per 32 rows: stage sz = two 8 KB Zbar half-chunks, then two stages of A_in chunks
           auto dw_half = [&]() {
             if (nB > 0) {
               mbar_wait(rb_free, (uint32_t)((nB - 1) & 1));   // the previous half has been drained
               tc_fence_after();
             }
             ++nB;
+#pragma unroll
             for (int g = 0; g < 4; ++g) {
-              const int sz = cc % TC_STAGES;
-              mbar_wait(&full[sz], (uint32_t)((cc / TC_STAGES) & 1));
+              const int sz = (3 * g) % TC_STAGES;
+              const uint32_t pz = rp ^ (uint32_t)(((3 * g) / TC_STAGES) & 1);
+              mbar_wait(&full[sz], pz);
 #pragma unroll
               for (int i = 0; i < 2; ++i) {
-                const int ca = cc + 1 + i, sa = ca % TC_STAGES;
-                mbar_wait(&full[sa], (uint32_t)((ca / TC_STAGES) & 1));
-                tc_fence_after();
+                const int ca = 3 * g + 1 + i, sa = ca % TC_STAGES;
+                mbar_wait(&full[sa], rp ^ (uint32_t)((ca / TC_STAGES) & 1));
 #pragma unroll
                 for (int kk = 0; kk < 2; ++kk) {
                   const int kstep = g * 4 + i * 2 + kk;   // 8 rows per MMA
-                  const uint64_t ad = umma_desc_mn(ring_addr + (uint32_t)sz * TC_STAGE_BYTES + (uint32_t)i * 8192u +
-                                                       (uint32_t)kk * 1024u,
-                                                   2048, 512);
-                  const uint64_t bd = umma_desc_mn(ring_addr + (uint32_t)sa * TC_STAGE_BYTES + (uint32_t)kk * 1024u,
-                                                   2048, 512);
-                  umma_tf32(tmem_base + 256u, ad, bd, idesc_mn, kstep > 0 ? 1u : 0u);
+                  umma_tf32(tmem_base + 256u, d_mn + (uint64_t)sz * STG + (uint64_t)(i * 512 + kk * 64),
+                            d_mn + (uint64_t)sa * STG + (uint64_t)(kk * 64), idesc_mn, kstep > 0 ? 1u : 0u);
                 }
                 umma_commit(&empty[sa]);
               }
               umma_commit(&empty[sz]);
-              cc += 3;
             }
+            rp ^= 1u;   // 12 chunks = 3 ring passes
             umma_commit(mma_done_b);
           };
           for (int l = L - 2; l >= 1; --l) {
@@ -430,6 +437,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     auto img_off = [&](int j, int b, int u) {
       return img_thr + (j >> 1) * TC_STAGE_FLOATS + (j & 1) * 256 + (b >> 1) * 512 + (((2 * (b & 1) + u) ^ (pp & 3)) << 3);
     };
+    int nzs = 0;  // Zbar spills published
     int mj = 0;   // adjoint / forward MMA jobs waited for
     int nbw = 0;  // weight-gradient half jobs drained
     TCT_DECL
@@ -438,10 +446,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       ++mj;
       tc_fence_after();
     };
-    auto signal_ready = [&]() {
+    auto signal_ready = [&]() {   // this thread's part of the operand image is written (and its TMEM reads are done)
       tc_fence_before();
-      fence_async_proxy();
+      fence_async_proxy_smem();
       mbar_arrive(op_ready);
+    };
+    auto publish_spill = [&](uint64_t* bar) {   // this thread's spill stores -> visible to the TMA engine at L2
+      __threadfence();
+      fence_async_proxy();
+      mbar_arrive(bar);
     };
     // all four jets of this thread's point for the 4 features of block b: v[j][2u+e]
     auto ld_block = [&](int b, float (&v)[4][4]) {
@@ -604,12 +617,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         TCT(1)
         if (l < L - 2) signal_ready();
       }
-      if (BWD) {
-        // the TMA engine reads the spills at L2: publish the generic-proxy stores at GPU scope first
-        __threadfence();
-        fence_async_proxy();
-        mbar_arrive(slab_ready);
-      }
+      if (BWD) publish_spill(slab_ready);
       tc_fence_before();
       worker_bar();
       TCT(3)
@@ -720,10 +728,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           if (L - 3 < TC_MAX_HH) db_block(dbl, b, ab[0]);
         }
       }
-      __threadfence();
-      fence_async_proxy();
-      mbar_arrive(zt_ready);
       signal_ready();                       // adjoint job of layer L-2 may start
+      publish_spill(&zt_ready[nzs++ & 1]);
       TCT(5)
       // ---- hidden layers L-2 .. 1, software-pipelined ----
       //   tensor core: adjoint job of layer l (TMEM columns 0..255), weight-gradient halves (columns 256..511)
@@ -762,33 +768,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           float* zdst = zimg + (size_t)((l - 1) % TC_ZBUFS) * TC_IMG;
           float* dbl = db_s + (size_t)(l >= 2 ? l - 2 : 0) * TC_H;
           const bool hidden = l > 1;
-          float act[4][4], nxt[4][4];
-          ld_img_block(aimg, 0, act);   // issued before the wait: the loads overlap the adjoint MMA
+          float act[TC_NBLK][4][4];
+#pragma unroll
+          for (int b = 0; b < TC_NBLK; ++b) ld_img_block(aimg, b, act[b]);   // in flight while the adjoint MMA runs
           wait_mma();
           TCT(9)
 #pragma unroll
           for (int b = 0; b < TC_NBLK; ++b) {
             float ab[4][4];
-            if (b < TC_NBLK - 1) ld_img_block(aimg, b + 1, nxt);
             ld_block(b, ab);
-            adjoint(ab, act);
+            adjoint(ab, act[b]);
             st_op_block(b, ab);
             if (hidden) {
               st_img_block(zdst, b, ab);
               if (l - 2 < TC_MAX_HH) db_block(dbl, b, ab[0]);
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-              for (int i = 0; i < 4; ++i) act[j][i] = nxt[j][i];
           }
         }
         TCT(10)
         if (l > 1) {
-          __threadfence();
-          fence_async_proxy();
-          mbar_arrive(zt_ready);
           signal_ready();                   // adjoint job of layer l-1 may start
+          publish_spill(&zt_ready[nzs++ & 1]);
         }
         TCT(6)
         if (l < L - 2) drain(l + 1, 1);
@@ -879,7 +879,7 @@ __global__ void pack_tc_kernel(const __grid_constant__ pinn_desc_t D, const floa
 // --------------------------------------------------------------------------------------- host side
 constexpr size_t tc_smem_bytes() {
   return (size_t)OP_BYTES + (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)TC_H * 8 * 4 + (size_t)8 * TC_H * 4 +
-         (size_t)TC_M * 8 * 4 + (size_t)TC_TP * 8 * 4 + (size_t)TC_MAX_HH * TC_H * 4 + PINN_NSUMS * 8 + (2 * TC_STAGES + 6) * 8 + 16;
+         (size_t)TC_M * 8 * 4 + (size_t)TC_TP * 8 * 4 + (size_t)TC_MAX_HH * TC_H * 4 + PINN_NSUMS * 8 + (2 * TC_STAGES + 7) * 8 + 16;
 }
 
 // Can this description run on the tensor-core kernel?  (otherwise the caller reports UNSUPPORTED)
