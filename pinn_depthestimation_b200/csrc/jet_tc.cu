@@ -55,7 +55,7 @@ constexpr int OP_LBO = TC_M * 16 + 64;     // 2112
 constexpr int OP_BYTES = (TC_H / 4) * OP_LBO;
 constexpr int TC_IMG = TC_M * TC_H;        // floats per spill image
 constexpr int TC_ZBUFS = 3;                // Zbar spill images in flight (layer l uses buffer l % 3)
-constexpr int TC_WCHUNKS = TC_H * TC_H * 4 / TC_STAGE_BYTES;   // 16 chunks per weight image
+constexpr int TC_WCHUNKS = TC_H * (TC_H / 2) * 4 / TC_STAGE_BYTES;   // 8 chunks per half-width weight image
 constexpr int TC_MAX_HH = 7;               // hidden->hidden layers whose bias gradients are staged in shared memory
 
 struct TcArgs {
@@ -84,15 +84,15 @@ __device__ __forceinline__ void fence_async_proxy_smem() { asm volatile("fence.p
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TC_WORKERS) : "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
                "r"(ncols)
                : "memory");
 }
 __device__ __forceinline__ void tmem_relinquish() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 // D[tmem] (+)= A[smem desc] * B[smem desc], TF32 inputs, FP32 accumulate; issued by ONE thread
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -101,15 +101,40 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       "{\n"
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// arrive on an mbarrier when all previously issued MMAs of this thread have completed
+// arrive on the mbarrier at this shared-memory offset in BOTH CTAs of the pair when all previously issued MMAs
+// of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
                : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared::cta pointer of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(p)), "r"(rank));
+  return ra;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// no ordering of this thread's own earlier accesses: for pure hand-offs (the relay), where a releasing arrive would
+// make every arrive wait for the round trip of the previous one
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
@@ -217,7 +242,7 @@ struct TileJets {  // output jets of one point in the [128 rows][8] area, row = 
 #endif
 
 template <bool BWD>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     jet_tc_kernel(const __grid_constant__ pinn_desc_t D, const __grid_constant__ TcArgs A) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* op = smem_raw;                                   // operand image (A or Zbar)
@@ -230,7 +255,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   double* red = reinterpret_cast<double*>(db_s + TC_MAX_HH * TC_H);  // [16]
   uint64_t* full = reinterpret_cast<uint64_t*>(red + PINN_NSUMS);  // [S]
   uint64_t* empty = full + TC_STAGES;                             // [S]
-  uint64_t* op_ready = empty + TC_STAGES;
+  uint64_t* full_peer = empty + TC_STAGES;                        // [S] leader only: the follower's stage has landed
+  uint64_t* op_ready = full_peer + TC_STAGES;
   uint64_t* mma_done = op_ready + 1;
   uint64_t* slab_ready = mma_done + 1;
   uint64_t* zt_ready = slab_ready + 1;   // [2], alternating per Zbar spill: the workers may run one spill ahead of the
@@ -245,8 +271,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const int d = D.widths[0], o = D.widths[L];
   const int NHH = L - 2;                      // hidden->hidden layers (tensor-core jobs per direction)
   const int kind = D.residual_kind;
-  const int my_tiles = (A.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // CTA pair: the two CTAs of a cluster work on two tiles in lock step.  Forward / adjoint jobs are ONE
+  // cta_group::2 MMA stream (M = 256: each CTA's 128 rows; each CTA streams only its 128-column half of the
+  // weights); the weight-gradient job of a layer contracts over the rows of BOTH tiles, CTA r owning the Zbar
+  // features [128 r, 128 r + 128) -- one drain per layer per CTA.
+  const uint32_t rank = cluster_ctarank();
+  const int pair = (int)blockIdx.x >> 1, n_pairs = (int)gridDim.x >> 1;
+  const int tile_pairs = (A.n_tiles + 1) >> 1;
+  const int my_tiles = (tile_pairs - pair + n_pairs - 1) / n_pairs;   // tile pairs this cluster processes
   float* slab = A.slab + (long long)blockIdx.x * A.slab_stride;  // P-images of a_0 .. a_{L-3}
+  const float* slab_pair[2] = {A.slab + (long long)(2 * pair) * A.slab_stride, A.slab + (long long)(2 * pair + 1) * A.slab_stride};
   float* zimg = slab + (size_t)(L - 2) * TC_IMG;                 // TC_ZBUFS P-images of Zbar
   const long long P0 = (long long)d * TC_H + TC_H;               // params of layer 0
   const long long PH = (long long)TC_H * TC_H + TC_H;            // params of a hidden->hidden layer
@@ -257,14 +291,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
+      mbar_init(&full_peer[s], 1);
     }
-    mbar_init(op_ready, TC_WORKERS);
+    // cross-CTA barriers count one elected arrival per worker warp of each CTA
+    mbar_init(op_ready, 2 * TC_WORKERS / 32);
     mbar_init(mma_done, 1);
-    mbar_init(slab_ready, TC_WORKERS);
-    mbar_init(&zt_ready[0], TC_WORKERS);
-    mbar_init(&zt_ready[1], TC_WORKERS);
+    mbar_init(slab_ready, 2 * TC_WORKERS / 32);
+    mbar_init(&zt_ready[0], 2 * TC_WORKERS / 32);
+    mbar_init(&zt_ready[1], 2 * TC_WORKERS / 32);
     mbar_init(mma_done_b, 1);
-    mbar_init(rb_free, TC_WORKERS);
+    mbar_init(rb_free, 2 * TC_WORKERS / 32);
     mbar_fence_init();
   }
   if (tid < PINN_NSUMS) red[tid] = 0.0;
@@ -283,11 +319,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();     // barriers of both CTAs are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == TC_WORKERS / 32) {
     // =========================================== producer ===========================================
+    // Both CTAs run the same load sequence; each streams ITS half of every operand:
+    //   forward / adjoint job: 8 stages = the 128-column half `rank` of the weight image (32 K-features per stage)
+    //   weight-gradient job:   16 stages = for tile 0 then tile 1 of the pair, per 16 rows the 4 panels `rank` of the
+    //                          Zbar chunk (A operand, its M half) and of the A_in chunk (B operand, its N half)
     if (lane == 0) {
       int pc = 0, nzt = 0;
       auto load = [&](const float* src) {
@@ -305,69 +346,85 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         tma_load_1d(ring + s * TC_STAGE_BYTES + TC_STAGE_BYTES / 2, src1, TC_STAGE_BYTES / 2, &full[s]);
         ++pc;
       };
+      const size_t half_off = (size_t)rank * (TC_H * TC_H / 2);
       for (int it = 0; it < my_tiles; ++it) {
         for (int hl = 0; hl < NHH; ++hl)
           for (int c = 0; c < TC_WCHUNKS; ++c)
-            load(A.packed + (size_t)hl * 2 * TC_H * TC_H + (size_t)c * TC_STAGE_FLOATS);
+            load(A.packed + (size_t)hl * 2 * TC_H * TC_H + half_off + (size_t)c * TC_STAGE_FLOATS);
         if (BWD) {
-          mbar_wait(slab_ready, (uint32_t)(it & 1));  // this tile's activation spills are written and fenced
-          // one weight-gradient half job = 128 Zbar features x 256 A_in features over the tile's 128 rows:
-          // per 32 rows one stage holding the half-h panels (8 KB) of two 16-row Zbar chunks, and two stages
-          // holding the two 16-row chunks of A_in
-          auto load_dw_half = [&](int l, int h) {
-            const float* zsrc = zimg + (size_t)(l % TC_ZBUFS) * TC_IMG + (size_t)h * (TC_STAGE_FLOATS / 2);
-            const float* asrc = slab + (size_t)(l - 1) * TC_IMG;
-            for (int g = 0; g < 4; ++g) {
-              load2(zsrc + (size_t)(2 * g) * TC_STAGE_FLOATS, zsrc + (size_t)(2 * g + 1) * TC_STAGE_FLOATS);
-              load(asrc + (size_t)(2 * g) * TC_STAGE_FLOATS);
-              load(asrc + (size_t)(2 * g + 1) * TC_STAGE_FLOATS);
-            }
-          };
+          mbar_wait(slab_ready, (uint32_t)(it & 1));  // both tiles' activation spills are written and fenced
           for (int l = L - 2; l >= 1; --l) {
             for (int c = 0; c < TC_WCHUNKS; ++c)       // adjoint job of layer l
-              load(A.packed + (size_t)(l - 1) * 2 * TC_H * TC_H + (size_t)TC_H * TC_H +
+              load(A.packed + (size_t)(l - 1) * 2 * TC_H * TC_H + (size_t)TC_H * TC_H + half_off +
                    (size_t)c * TC_STAGE_FLOATS);
-            if (l < L - 2) load_dw_half(l + 1, 1);
-            mbar_wait(&zt_ready[nzt & 1], (uint32_t)((nzt >> 1) & 1));  // Zbar_l has been spilled
+            mbar_wait(&zt_ready[nzt & 1], (uint32_t)((nzt >> 1) & 1));  // Zbar_l of both tiles has been spilled
             ++nzt;
-            load_dw_half(l, 0);
+            for (int t = 0; t < 2; ++t) {
+              const float* zsrc = slab_pair[t] + (size_t)(L - 2 + l % TC_ZBUFS) * TC_IMG + (size_t)rank * (TC_STAGE_FLOATS / 2);
+              const float* asrc = slab_pair[t] + (size_t)(l - 1) * TC_IMG + (size_t)rank * (TC_STAGE_FLOATS / 2);
+              for (int r = 0; r < 8; ++r)
+                load2(zsrc + (size_t)r * TC_STAGE_FLOATS, asrc + (size_t)r * TC_STAGE_FLOATS);
+            }
           }
-          load_dw_half(1, 1);
         }
       }
     }
   } else if (warp == TC_WORKERS / 32 + 1) {
     // =========================================== MMA issuer =========================================
-    if (lane == 0) {
-      constexpr uint32_t idesc_k = umma_idesc(TC_M, TC_H, 0, 0);
-      constexpr uint32_t idesc_mn = umma_idesc(TC_M, TC_H, 1, 1);
+    if (lane == 0 && rank != 0) {
+      // follower: relay "my stage has landed" to the leader's issuer (1-D bulk copies cannot signal a peer barrier)
+      const int per_tile = NHH * TC_WCHUNKS + (BWD ? NHH * (TC_WCHUNKS + 16) : 0);
+      const long long total = (long long)my_tiles * per_tile;
+      uint32_t fp[TC_STAGES];
+#pragma unroll
+      for (int s = 0; s < TC_STAGES; ++s) fp[s] = mapa_u32(&full_peer[s], 0);
+      uint32_t par = 0;
+      for (long long c = 0; c < total; c += TC_STAGES) {
+#pragma unroll
+        for (int s = 0; s < TC_STAGES; ++s) {
+          mbar_wait(&full[s], par);
+          mbar_arrive_cluster_relaxed(fp[s]);
+        }
+        par ^= 1u;
+      }
+    }
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc_k = umma_idesc(2 * TC_M, TC_H, 0, 0);
+      constexpr uint32_t idesc_mn = umma_idesc(2 * TC_M, TC_H, 1, 1);
       // The issue loop runs on ONE thread: every scalar instruction in it is on the tensor pipe's critical path
       // (a 128x256x8 TF32 MMA retires in ~130 cycles, tools/mma_rate_probe.cu).  Descriptors are therefore
       // built once; per MMA only the 14-bit start-address field (16-byte units) advances by a compile-time
       // constant.  Every job consumes a multiple of TC_STAGES ring stages, so stage indices are constants too.
-      static_assert(TC_WCHUNKS % TC_STAGES == 0 && 12 % TC_STAGES == 0, "jobs must keep the ring stage index aligned");
+      static_assert(TC_WCHUNKS % TC_STAGES == 0 && 16 % TC_STAGES == 0, "jobs must keep the ring stage index aligned");
       const uint64_t ad_op = umma_desc(smem_u32(op), OP_LBO, 128);            // + kstep * (2 * OP_LBO / 16)
-      const uint64_t bd_k = umma_desc(smem_u32(ring), TC_H * 16, 128);        // K-major weight chunk in stage 0
-      const uint64_t d_mn = umma_desc_mn(smem_u32(ring), 2048, 512);          // MN-major spill chunk in stage 0
+      const uint64_t bd_k = umma_desc(smem_u32(ring), (TC_H / 2) * 16, 128);  // K-major half-width weight chunk in stage 0
+      const uint64_t d_mn = umma_desc_mn(smem_u32(ring), 2048, 512);          // MN-major spill half-chunk in stage 0
       constexpr uint64_t STG = TC_STAGE_BYTES / 16;
       uint32_t rp = 0;      // parity of the ring pass (flips every TC_STAGES chunks)
       int jobs = 0, nB = 0;
+#ifdef PINN_TC_DEBUG
+      long long iw_ready = 0, iw_full = 0, iw_peer = 0, iw_rb = 0, i_gemm = 0, i_dw = 0, it0;
+#define ITM(acc, stmt) { const long long a_ = clock64(); stmt; acc += clock64() - a_; }
+#else
+#define ITM(acc, stmt) stmt;
+#endif
       auto wait_ready = [&]() {
-        mbar_wait(op_ready, (uint32_t)(jobs & 1));
+        ITM(iw_ready, mbar_wait(op_ready, (uint32_t)(jobs & 1)))
         ++jobs;
         tc_fence_after();
       };
-      // D[128 x 256] = OP (K-major, 256 features) * image chunks (K-major)
+      // D[256 x 256] = OP (K-major, 256 features; 128 rows in each CTA) * weight half-images (K-major, 128 columns in each CTA)
       auto gemm_k = [&]() {
 #pragma unroll
         for (int c = 0; c < TC_WCHUNKS; ++c) {
           const int s = c % TC_STAGES;
-          mbar_wait(&full[s], rp);
+          ITM(iw_full, mbar_wait(&full[s], rp))
+          ITM(iw_peer, mbar_wait(&full_peer[s], rp))
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-            const int kstep = c * 2 + kk;  // 8 contraction features per MMA = two 16-byte K chunks
+          for (int kk = 0; kk < 4; ++kk) {
+            const int kstep = c * 4 + kk;  // 8 contraction features per MMA = two 16-byte K chunks
             umma_tf32(tmem_base, ad_op + (uint64_t)(kstep * (2 * OP_LBO / 16)),
-                      bd_k + (uint64_t)s * STG + (uint64_t)(kk * (2 * TC_H * 16 / 16)), idesc_k, kstep > 0 ? 1u : 0u);
+                      bd_k + (uint64_t)s * STG + (uint64_t)(kk * (2 * (TC_H / 2) * 16 / 16)), idesc_k, kstep > 0 ? 1u : 0u);
           }
           umma_commit(&empty[s]);
           if (s == TC_STAGES - 1) rp ^= 1u;
@@ -377,48 +434,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       for (int it = 0; it < my_tiles; ++it) {
         for (int hl = 0; hl < NHH; ++hl) {
           wait_ready();
-          gemm_k();
+          ITM(i_gemm, gemm_k())
         }
         if (BWD) {
-          // weight-gradient half job into TMEM columns 256..511: both operands MN-major (contraction over rows);
-          // per 32 rows: stage sz = two 8 KB Zbar half-chunks, then two stages of A_in chunks
-          auto dw_half = [&]() {
+          // weight-gradient job of one layer into TMEM columns 256..511: both operands MN-major (contraction over
+          // the 2 x 128 rows of the pair's tiles); per stage = 16 rows: [Zbar half-chunk 8 KB][A_in half-chunk 8 KB]
+          auto dw_job = [&]() {
             if (nB > 0) {
-              mbar_wait(rb_free, (uint32_t)((nB - 1) & 1));   // the previous half has been drained
+              ITM(iw_rb, mbar_wait(rb_free, (uint32_t)((nB - 1) & 1)))   // the previous accumulator has been drained in both CTAs
               tc_fence_after();
             }
             ++nB;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int sz = (3 * g) % TC_STAGES;
-              const uint32_t pz = rp ^ (uint32_t)(((3 * g) / TC_STAGES) & 1);
-              mbar_wait(&full[sz], pz);
+            for (int q = 0; q < 16; ++q) {
+              const int s = q % TC_STAGES;
+              ITM(iw_full, mbar_wait(&full[s], rp))
+              ITM(iw_peer, mbar_wait(&full_peer[s], rp))
 #pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                const int ca = 3 * g + 1 + i, sa = ca % TC_STAGES;
-                mbar_wait(&full[sa], rp ^ (uint32_t)((ca / TC_STAGES) & 1));
-#pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                  const int kstep = g * 4 + i * 2 + kk;   // 8 rows per MMA
-                  umma_tf32(tmem_base + 256u, d_mn + (uint64_t)sz * STG + (uint64_t)(i * 512 + kk * 64),
-                            d_mn + (uint64_t)sa * STG + (uint64_t)(kk * 64), idesc_mn, kstep > 0 ? 1u : 0u);
-                }
-                umma_commit(&empty[sa]);
-              }
-              umma_commit(&empty[sz]);
+              for (int kk = 0; kk < 2; ++kk)
+                umma_tf32(tmem_base + 256u, d_mn + (uint64_t)s * STG + (uint64_t)(kk * 64),
+                          d_mn + (uint64_t)s * STG + (uint64_t)(512 + kk * 64), idesc_mn, (q > 0 || kk > 0) ? 1u : 0u);
+              umma_commit(&empty[s]);
+              if (s == TC_STAGES - 1) rp ^= 1u;
             }
-            rp ^= 1u;   // 12 chunks = 3 ring passes
             umma_commit(mma_done_b);
           };
           for (int l = L - 2; l >= 1; --l) {
-            wait_ready();                      // Zbar_l is in the operand image, columns 0..255 are drained
-            gemm_k();                          // adjoint of the layer input
-            if (l < L - 2) dw_half();          // layer l+1, features 128..255
-            dw_half();                         // layer l,   features 0..127
+            wait_ready();                      // Zbar_l is in both operand images, columns 0..255 are drained
+            ITM(i_gemm, gemm_k())              // adjoint of the layer input
+            ITM(i_dw, dw_job())                // weight gradient of layer l
           }
-          dw_half();                           // layer 1,   features 128..255
         }
       }
+#ifdef PINN_TC_DEBUG
+      if (blockIdx.x == 0)
+        printf("TC issuer (cycles per tile pair): wait op_ready %lld | gemm jobs %lld (14) | dW jobs %lld (7) | of which wait full %lld, wait peer %lld, wait rb_free %lld\n",
+               iw_ready / my_tiles, i_gemm / my_tiles, i_dw / my_tiles, iw_full / my_tiles, iw_peer / my_tiles, iw_rb / my_tiles);
+#endif
     }
   } else {
     // =========================================== workers ============================================
@@ -446,15 +498,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       ++mj;
       tc_fence_after();
     };
+    // cross-CTA signalling: every thread fences, one elected lane per warp arrives
+    const uint32_t op_ready_leader = mapa_u32(op_ready, 0), rb_free_leader = mapa_u32(rb_free, 0);
     auto signal_ready = [&]() {   // this thread's part of the operand image is written (and its TMEM reads are done)
       tc_fence_before();
-      fence_async_proxy_smem();
-      mbar_arrive(op_ready);
+      fence_async_proxy();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(op_ready_leader);
     };
-    auto publish_spill = [&](uint64_t* bar) {   // this thread's spill stores -> visible to the TMA engine at L2
+    auto publish_spill = [&](uint64_t* bar) {   // this thread's spill stores -> visible to both CTAs' TMA engines at L2
       __threadfence();
       fence_async_proxy();
-      mbar_arrive(bar);
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_cluster(mapa_u32(bar, 0));
+        mbar_arrive_cluster(mapa_u32(bar, 1));
+      }
     };
     // all four jets of this thread's point for the 4 features of block b: v[j][2u+e]
     auto ld_block = [&](int b, float (&v)[4][4]) {
@@ -547,7 +606,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     };
 
     for (int it = 0; it < my_tiles; ++it) {
-      const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
+      const long long tile = 2ll * (pair + (long long)it * n_pairs) + rank;   // may lie past the end: an all-padding tile
       const long long p0 = tile * TC_TP;
       for (int i = tid; i < TC_TP * 8; i += TC_WORKERS) {
         const int pq = i >> 3, c = i & 7;
@@ -731,20 +790,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       signal_ready();                       // adjoint job of layer L-2 may start
       publish_spill(&zt_ready[nzs++ & 1]);
       TCT(5)
-      // ---- hidden layers L-2 .. 1, software-pipelined ----
-      //   tensor core: adjoint job of layer l (TMEM columns 0..255), weight-gradient halves (columns 256..511)
-      //   workers:     adjoint epilogue of layer l (Zbar_{l-1} -> operand image + spill) | drain half 1 of layer
-      //                l+1 | drain half 0 of layer l
-      // drain TMEM columns 256..511 = dW rows [128h, 128h+128) of layer l.  16x256b loads: the 4 lanes of a
+      // ---- hidden layers L-2 .. 1 ----
+      //   tensor core: adjoint job of layer l (TMEM columns 0..255), then the weight-gradient job of layer l over the
+      //                rows of both tiles of the pair (columns 256..511)
+      //   workers:     adjoint epilogue of layer l (Zbar_{l-1} -> operand image + spill) | drain of layer l
+      // drain TMEM columns 256..511 = dW rows [128 rank, 128 rank + 128) of layer l.  16x256b loads: the 4 lanes of a
       // quad hold 8 consecutive columns of one row, so every RED instruction updates full 32-byte sectors
-      auto drain = [&](int l, int h) {
+      auto drain = [&](int l) {
         mbar_wait(mma_done_b, (uint32_t)(nbw & 1));
         ++nbw;
         tc_fence_after();
         const long long poff = P0 + (long long)(l - 1) * PH;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          const int row = h * 128 + sp * 32 + g * 16 + (lane >> 2);
+          const int row = (int)rank * 128 + sp * 32 + g * 16 + (lane >> 2);
           float* grow = A.grad + poff + (long long)row * TC_H + cbase + 2 * (lane & 3);
           const uint32_t ta = tmem_base + ((uint32_t)(sp * 32 + g * 16) << 16) + (uint32_t)(256 + cbase);
 #pragma unroll
@@ -759,7 +818,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
         }
         tc_fence_before();
-        mbar_arrive(rb_free);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(rb_free_leader);
       };
       for (int l = L - 2; l >= 1; --l) {
         // adjoint through the activation of layer l-1 -> Zbar_{l-1} in place (+ spill for its weight gradient)
@@ -791,12 +851,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           publish_spill(&zt_ready[nzs++ & 1]);
         }
         TCT(6)
-        if (l < L - 2) drain(l + 1, 1);
-        TCT(8)
-        drain(l, 0);
+        drain(l);
         TCT(7)
       }
-      drain(1, 1);
       tc_fence_before();
       worker_bar();
       TCT(8)
@@ -851,35 +908,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   // ---------------- teardown ----------------
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();     // the peer may still signal this CTA's barriers / read its shared memory until here
   tc_fence_after();
   if (warp == TC_WORKERS / 32 + 1) tmem_dealloc(tmem_base, 512);
   if (tid < PINN_NSUMS && A.sums && red[tid] != 0.0) atomicAdd(A.sums + tid, red[tid]);
 }
 
-// Weight images for the tensor-core jobs, TF32-rounded: layer hl (= linear layer hl+1)
-//   Wk[(k/4)*H*4 + n*4 + k%4] = W[n][k]   (forward:  B operand, rows n, contraction k)
-//   WT[(n/4)*H*4 + k*4 + n%4] = W[n][k]   (adjoint:  B operand, rows k, contraction n)
+// Weight images for the tensor-core jobs, TF32-rounded.  Layer hl (= linear layer hl+1) has four half-width images
+// of 128 KB, [direction][half]: each is the B operand one CTA of the pair streams (its 128 of the 256 N columns),
+// in 16 KB chunks of 32 contraction features laid out [k/4 (8)][n (128)][k%4] (K-major, no swizzle):
+//   forward:  B[n][k] = W[n][k]     half = n / 128   (rows n = output feature, contraction k = input feature)
+//   adjoint:  B[n][k] = W[k][n]     half = n / 128   (rows n = input feature,  contraction k = output feature)
 __global__ void pack_tc_kernel(const __grid_constant__ pinn_desc_t D, const float* __restrict__ params,
                                float* __restrict__ packed) {
   const int hl = blockIdx.y;
   const int d = D.widths[0];
   const long long poff = (long long)d * TC_H + TC_H + (long long)hl * ((long long)TC_H * TC_H + TC_H);
-  float* wk = packed + (size_t)hl * 2 * TC_H * TC_H;
-  float* wt = wk + (size_t)TC_H * TC_H;
+  float* fwd = packed + (size_t)hl * 2 * TC_H * TC_H;
+  float* adj = fwd + (size_t)TC_H * TC_H;
+  auto at = [](int n, int k) {   // float offset of B[n][k] inside its direction's two half-images
+    return (size_t)(n >> 7) * (TC_H * TC_H / 2) + (size_t)(k >> 5) * TC_STAGE_FLOATS + (size_t)((k & 31) >> 2) * 512 +
+           (size_t)(n & 127) * 4 + (size_t)(k & 3);
+  };
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < TC_H * TC_H; i += gridDim.x * blockDim.x) {
     const int n = i / TC_H, k = i - n * TC_H;
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(params[poff + i]));
     const float w = __uint_as_float(r);
-    wk[(size_t)(k >> 2) * TC_H * 4 + n * 4 + (k & 3)] = w;
-    wt[(size_t)(n >> 2) * TC_H * 4 + k * 4 + (n & 3)] = w;
+    fwd[at(n, k)] = w;
+    adj[at(k, n)] = w;
   }
 }
 
 // --------------------------------------------------------------------------------------- host side
 constexpr size_t tc_smem_bytes() {
   return (size_t)OP_BYTES + (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)TC_H * 8 * 4 + (size_t)8 * TC_H * 4 +
-         (size_t)TC_M * 8 * 4 + (size_t)TC_TP * 8 * 4 + (size_t)TC_MAX_HH * TC_H * 4 + PINN_NSUMS * 8 + (2 * TC_STAGES + 7) * 8 + 16;
+         (size_t)TC_M * 8 * 4 + (size_t)TC_TP * 8 * 4 + (size_t)TC_MAX_HH * TC_H * 4 + PINN_NSUMS * 8 + (3 * TC_STAGES + 7) * 8 + 16;
 }
 
 // Can this description run on the tensor-core kernel?  (otherwise the caller reports UNSUPPORTED)
@@ -900,8 +964,10 @@ int tc_workspace(const pinn_desc_t* D, long long n_points, int sms, size_t* pack
                  long long* slab_stride, int* grid) {
   const int L = D->n_linear;
   long long tiles = (n_points + TC_TP - 1) / TC_TP;
-  long long g = tiles < sms ? tiles : sms;
-  if (g < 1) g = 1;
+  long long pairs = (tiles + 1) / 2;
+  if (pairs > sms / 2) pairs = sms / 2;
+  if (pairs < 1) pairs = 1;
+  long long g = 2 * pairs;   // CTA pairs (clusters of 2)
   *grid = (int)g;
   *packed_bytes = (size_t)(L - 2) * 2 * TC_H * TC_H * 4;
   *slab_stride = (long long)((L - 2) + TC_ZBUFS) * TC_IMG;   // P-images of (L-2) layer outputs + the Zbar spills in flight
