@@ -371,20 +371,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     }
   } else if (warp == TC_WORKERS / 32 + 1) {
     // =========================================== MMA issuer =========================================
-    if (lane == 0 && rank != 0) {
-      // follower: relay "my stage has landed" to the leader's issuer (1-D bulk copies cannot signal a peer barrier)
+    if (lane < TC_STAGES && rank != 0) {
+      // follower: relay "my stage has landed" to the leader's issuer (1-D bulk copies cannot signal a peer barrier);
+      // one lane per ring stage so the hand-offs of different stages overlap
       const int per_tile = NHH * TC_WCHUNKS + (BWD ? NHH * (TC_WCHUNKS + 16) : 0);
-      const long long total = (long long)my_tiles * per_tile;
-      uint32_t fp[TC_STAGES];
-#pragma unroll
-      for (int s = 0; s < TC_STAGES; ++s) fp[s] = mapa_u32(&full_peer[s], 0);
+      const long long passes = (long long)my_tiles * per_tile / TC_STAGES;
+      const uint32_t fp = mapa_u32(&full_peer[lane], 0);
       uint32_t par = 0;
-      for (long long c = 0; c < total; c += TC_STAGES) {
-#pragma unroll
-        for (int s = 0; s < TC_STAGES; ++s) {
-          mbar_wait(&full[s], par);
-          mbar_arrive_cluster_relaxed(fp[s]);
-        }
+      for (long long c = 0; c < passes; ++c) {
+        mbar_wait(&full[lane], par);
+        mbar_arrive_cluster_relaxed(fp);
         par ^= 1u;
       }
     }
@@ -500,19 +496,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     };
     // cross-CTA signalling: every thread fences, one elected lane per warp arrives
     const uint32_t op_ready_leader = mapa_u32(op_ready, 0), rb_free_leader = mapa_u32(rb_free, 0);
+    // The operand image is read by this SM's own tensor core only, so a CTA-scope proxy fence per thread is enough;
+    // the arrive itself is relaxed: a releasing arrive would first wait for this thread's spill stores to reach L2.
     auto signal_ready = [&]() {   // this thread's part of the operand image is written (and its TMEM reads are done)
       tc_fence_before();
-      fence_async_proxy();
+      fence_async_proxy_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(op_ready_leader);
+      if (lane == 0) mbar_arrive_cluster_relaxed(op_ready_leader);
     };
     auto publish_spill = [&](uint64_t* bar) {   // this thread's spill stores -> visible to both CTAs' TMA engines at L2
-      __threadfence();
-      fence_async_proxy();
+      __threadfence();          // every thread: its own stores are performed at GPU scope ...
+      fence_async_proxy();      // ... and ordered before async-proxy (TMA) reads
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive_cluster(mapa_u32(bar, 0));
-        mbar_arrive_cluster(mapa_u32(bar, 1));
+      if (lane == 0) {          // the fences above did the ordering; the arrives are plain hand-offs
+        mbar_arrive_cluster_relaxed(mapa_u32(bar, 0));
+        mbar_arrive_cluster_relaxed(mapa_u32(bar, 1));
       }
     };
     // all four jets of this thread's point for the 4 features of block b: v[j][2u+e]
@@ -819,7 +817,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(rb_free_leader);
+        if (lane == 0) mbar_arrive_cluster_relaxed(rb_free_leader);   // (a releasing arrive would wait for the REDs)
       };
       for (int l = L - 2; l >= 1; --l) {
         // adjoint through the activation of layer l-1 -> Zbar_{l-1} in place (+ spill for its weight gradient)
