@@ -27,13 +27,15 @@
 // Operand image in shared memory (K-major, no swizzle): element (row m, feature f) at byte
 //   (f/4)*OP_LBO + m*16 + (f%4)*4, OP_LBO = 128*16 + 64: the canonical K-major UMMA layout with
 //   LBO = OP_LBO, SBO = 128; the 64-byte pad makes the 8-byte jets-in-thread accesses conflict-free.
-// Spill image in global memory ("P-image", 128 KB per layer per tile): 16-row chunks of 16 KB, each
-//   [8 panels of 32 features][16 rows][128 B] with the 32-byte units of a row XOR-swizzled by (row % 4):
-//   exactly the MN-major SWIZZLE_128B_BASE32B shared-memory layout (LBO 2048 between panels, SBO 512
-//   between 4-row atoms), the only MN-major layout kind::tf32 accepts (tools/umma_mn_probe.cu).  It is
-//   row-major per panel, so the epilogue threads write it straight from registers in full 32-byte sectors
-//   and read it back the same way in the reverse sweep; one image serves the adjoint epilogue AND, streamed
-//   back by TMA, the weight-gradient contraction over rows -- no transposition pass anywhere.
+// Spill image in global memory (G_l, 256 KB per hidden layer l per tile) = the two operands of the weight-gradient
+//   job of layer l, Zbar_l (written in the reverse sweep) and a_{l-1} (written in the forward sweep), in 16-row chunks
+//   of 32 KB: [feature half 0: Zbar 8 KB | a 8 KB][feature half 1: Zbar 8 KB | a 8 KB], each 8 KB piece =
+//   [4 panels of 32 features][16 rows][128 B] with the 32-byte units of a row XOR-swizzled by (row % 4): exactly the
+//   MN-major SWIZZLE_128B_BASE32B shared-memory layout (LBO 2048 between panels, SBO 512 between 4-row atoms), the
+//   only MN-major layout kind::tf32 accepts (tools/umma_mn_probe.cu).  It is row-major per panel, so the epilogue
+//   threads write it straight from registers in full 32-byte sectors and read a_{l-1} back the same way in the
+//   reverse sweep; one CTA of the pair needs exactly one contiguous 16 KB piece per 16 rows (one TMA copy per ring
+//   stage) -- no transposition pass anywhere.
 #include "common.cuh"
 #include "residual.cuh"
 
@@ -48,19 +50,19 @@ constexpr int TC_THREADS = TC_WORKERS + 64;
 constexpr int TC_WCOLS = TC_H / TC_WPS;    // columns of a 128x256 accumulator owned by one worker warp
 constexpr int TC_NBLK = TC_WCOLS / 16;     // 16-column blocks per worker warp
 constexpr int TC_PARTS = TC_WORKERS / TC_H;  // worker threads per feature in the thread-per-feature phases
-constexpr int TC_STAGES = 4;
+constexpr int TC_STAGES = 5;
 constexpr int TC_STAGE_BYTES = 16384;
 constexpr int TC_STAGE_FLOATS = TC_STAGE_BYTES / 4;
 constexpr int OP_LBO = TC_M * 16 + 64;     // 2112
 constexpr int OP_BYTES = (TC_H / 4) * OP_LBO;
-constexpr int TC_IMG = TC_M * TC_H;        // floats per spill image
-constexpr int TC_ZBUFS = 3;                // Zbar spill images in flight (layer l uses buffer l % 3)
+constexpr int TC_IMG = TC_M * TC_H;        // floats per spill image (one quantity of one layer of one tile)
+constexpr int TC_GIMG = 2 * TC_IMG;        // floats per weight-gradient operand image (Zbar_l and a_{l-1} interleaved)
 constexpr int TC_WCHUNKS = TC_H * (TC_H / 2) * 4 / TC_STAGE_BYTES;   // 8 chunks per half-width weight image
 constexpr int TC_MAX_HH = 7;               // hidden->hidden layers whose bias gradients are staged in shared memory
 
 struct TcArgs {
   const float* params;
-  const float* packed;   // per hidden->hidden layer: Wk image [k/4][n][k%4], then WT image [n/4][k][n%4]
+  const float* packed;   // per hidden->hidden layer 4 half-width weight images; then W0 padded [H][8], Wlast padded [8][H]
   const float* inputs;
   const float* targets;
   const float* mask_count;
@@ -68,7 +70,7 @@ struct TcArgs {
   double* sums;
   float* out;
   float* dout[PINN_MAX_DIRS];
-  float* slab;            // per CTA: (L-2) P-images of layer outputs, then TC_ZBUFS P-images of Zbar
+  float* slab;            // per CTA: (L-2) weight-gradient operand images G_l = {Zbar_l, a_{l-1}}
   long long slab_stride;  // floats per CTA
   long long n_points;
   int n_tiles;
@@ -247,9 +249,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* op = smem_raw;                                   // operand image (A or Zbar)
   unsigned char* ring = op + OP_BYTES;
-  float* w0s = reinterpret_cast<float*>(ring + TC_STAGES * TC_STAGE_BYTES);  // [H][8]  W0[f][c]
-  float* wls = w0s + TC_H * 8;                                    // [8][H]  Wlast[c][f]
-  float* outs = wls + 8 * TC_H;                                   // [128][8] output jets / seeds
+  float* outs = reinterpret_cast<float*>(ring + TC_STAGES * TC_STAGE_BYTES);  // [128][8] output jets / seeds
   float* xin = outs + TC_M * 8;                                   // [32][8]
   float* db_s = xin + TC_TP * 8;                                  // [TC_MAX_HH][H] hidden-layer bias gradients
   double* red = reinterpret_cast<double*>(db_s + TC_MAX_HH * TC_H);  // [16]
@@ -279,12 +279,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   const int pair = (int)blockIdx.x >> 1, n_pairs = (int)gridDim.x >> 1;
   const int tile_pairs = (A.n_tiles + 1) >> 1;
   const int my_tiles = (tile_pairs - pair + n_pairs - 1) / n_pairs;   // tile pairs this cluster processes
-  float* slab = A.slab + (long long)blockIdx.x * A.slab_stride;  // P-images of a_0 .. a_{L-3}
+  float* slab = A.slab + (long long)blockIdx.x * A.slab_stride;  // G_1 .. G_{L-2} of this CTA's tile
   const float* slab_pair[2] = {A.slab + (long long)(2 * pair) * A.slab_stride, A.slab + (long long)(2 * pair + 1) * A.slab_stride};
-  float* zimg = slab + (size_t)(L - 2) * TC_IMG;                 // TC_ZBUFS P-images of Zbar
   const long long P0 = (long long)d * TC_H + TC_H;               // params of layer 0
   const long long PH = (long long)TC_H * TC_H + TC_H;            // params of a hidden->hidden layer
   const long long poffL = P0 + (long long)NHH * PH;              // params offset of the last layer
+  const float* w0p = A.packed + (size_t)NHH * 2 * TC_H * TC_H;   // [H][8]  W0[f][c], zero-padded (L1-resident)
+  const float* wlp = w0p + TC_H * 8;                             // [8][H]  Wlast[c][f], zero-padded
 
   // ---------------- one-time setup ----------------
   if (tid == 0) {
@@ -304,14 +305,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     mbar_fence_init();
   }
   if (tid < PINN_NSUMS) red[tid] = 0.0;
-  for (int i = tid; i < TC_H * 8; i += TC_THREADS) {
-    const int f = i >> 3, c = i & 7;
-    w0s[i] = c < d ? A.params[(long long)f * d + c] : 0.f;
-  }
-  for (int i = tid; i < 8 * TC_H; i += TC_THREADS) {
-    const int c = i / TC_H, f = i - c * TC_H;
-    wls[i] = c < o ? A.params[poffL + (long long)c * TC_H + f] : 0.f;
-  }
   for (int i = tid; i < TC_MAX_HH * TC_H; i += TC_THREADS) db_s[i] = 0.f;
   if (warp == TC_WORKERS / 32 + 1) {
     tmem_alloc(tmem_ptr, 512);
@@ -327,24 +320,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     // =========================================== producer ===========================================
     // Both CTAs run the same load sequence; each streams ITS half of every operand:
     //   forward / adjoint job: 8 stages = the 128-column half `rank` of the weight image (32 K-features per stage)
-    //   weight-gradient job:   16 stages = for tile 0 then tile 1 of the pair, per 16 rows the 4 panels `rank` of the
-    //                          Zbar chunk (A operand, its M half) and of the A_in chunk (B operand, its N half)
+    //   weight-gradient job:   16 stages = for tile 0 then tile 1 of the pair, per 16 rows the 16 KB piece `rank` of G_l:
+    //                          4 panels of Zbar (A operand, its M half) and 4 panels of a_{l-1} (B operand, its N half)
     if (lane == 0) {
-      int pc = 0, nzt = 0;
+      int ps = 0, nzt = 0;
+      uint32_t pph = 1;     // parity to wait for on empty[ps] (first pass: fresh barriers count as released)
       auto load = [&](const float* src) {
-        const int s = pc % TC_STAGES;
-        mbar_wait(&empty[s], (uint32_t)(((pc / TC_STAGES) & 1) ^ 1));
-        mbar_expect_tx(&full[s], TC_STAGE_BYTES);
-        tma_load_1d(ring + s * TC_STAGE_BYTES, src, TC_STAGE_BYTES, &full[s]);
-        ++pc;
-      };
-      auto load2 = [&](const float* src0, const float* src1) {   // two 8 KB pieces into one stage
-        const int s = pc % TC_STAGES;
-        mbar_wait(&empty[s], (uint32_t)(((pc / TC_STAGES) & 1) ^ 1));
-        mbar_expect_tx(&full[s], TC_STAGE_BYTES);
-        tma_load_1d(ring + s * TC_STAGE_BYTES, src0, TC_STAGE_BYTES / 2, &full[s]);
-        tma_load_1d(ring + s * TC_STAGE_BYTES + TC_STAGE_BYTES / 2, src1, TC_STAGE_BYTES / 2, &full[s]);
-        ++pc;
+        mbar_wait(&empty[ps], pph);
+        mbar_expect_tx(&full[ps], TC_STAGE_BYTES);
+        tma_load_1d(ring + ps * TC_STAGE_BYTES, src, TC_STAGE_BYTES, &full[ps]);
+        if (++ps == TC_STAGES) ps = 0, pph ^= 1u;
       };
       const size_t half_off = (size_t)rank * (TC_H * TC_H / 2);
       for (int it = 0; it < my_tiles; ++it) {
@@ -360,10 +345,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             mbar_wait(&zt_ready[nzt & 1], (uint32_t)((nzt >> 1) & 1));  // Zbar_l of both tiles has been spilled
             ++nzt;
             for (int t = 0; t < 2; ++t) {
-              const float* zsrc = slab_pair[t] + (size_t)(L - 2 + l % TC_ZBUFS) * TC_IMG + (size_t)rank * (TC_STAGE_FLOATS / 2);
-              const float* asrc = slab_pair[t] + (size_t)(l - 1) * TC_IMG + (size_t)rank * (TC_STAGE_FLOATS / 2);
-              for (int r = 0; r < 8; ++r)
-                load2(zsrc + (size_t)r * TC_STAGE_FLOATS, asrc + (size_t)r * TC_STAGE_FLOATS);
+              const float* gsrc = slab_pair[t] + (size_t)(l - 1) * TC_GIMG + (size_t)rank * TC_STAGE_FLOATS;
+              for (int r = 0; r < 8; ++r) load(gsrc + (size_t)r * 2 * TC_STAGE_FLOATS);
             }
           }
         }
@@ -375,7 +358,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       // follower: relay "my stage has landed" to the leader's issuer (1-D bulk copies cannot signal a peer barrier);
       // one lane per ring stage so the hand-offs of different stages overlap
       const int per_tile = NHH * TC_WCHUNKS + (BWD ? NHH * (TC_WCHUNKS + 16) : 0);
-      const long long passes = (long long)my_tiles * per_tile / TC_STAGES;
+      const long long total = (long long)my_tiles * per_tile;
+      const long long passes = (total - lane + TC_STAGES - 1) / TC_STAGES;
       const uint32_t fp = mapa_u32(&full_peer[lane], 0);
       uint32_t par = 0;
       for (long long c = 0; c < passes; ++c) {
@@ -390,16 +374,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       // The issue loop runs on ONE thread: every scalar instruction in it is on the tensor pipe's critical path
       // (a 128x256x8 TF32 MMA retires in ~130 cycles, tools/mma_rate_probe.cu).  Descriptors are therefore
       // built once; per MMA only the 14-bit start-address field (16-byte units) advances by a compile-time
-      // constant.  Every job consumes a multiple of TC_STAGES ring stages, so stage indices are constants too.
-      static_assert(TC_WCHUNKS % TC_STAGES == 0 && 16 % TC_STAGES == 0, "jobs must keep the ring stage index aligned");
+      // constant; the ring stage index is a small running counter.
       const uint64_t ad_op = umma_desc(smem_u32(op), OP_LBO, 128);            // + kstep * (2 * OP_LBO / 16)
       const uint64_t bd_k = umma_desc(smem_u32(ring), (TC_H / 2) * 16, 128);  // K-major half-width weight chunk in stage 0
       const uint64_t d_mn = umma_desc_mn(smem_u32(ring), 2048, 512);          // MN-major spill half-chunk in stage 0
       constexpr uint64_t STG = TC_STAGE_BYTES / 16;
       uint32_t rp = 0;      // parity of the ring pass (flips every TC_STAGES chunks)
+      uint32_t rs = 0;      // ring stage of the next chunk
       int jobs = 0, nB = 0;
 #ifdef PINN_TC_DEBUG
-      long long iw_ready = 0, iw_full = 0, iw_peer = 0, iw_rb = 0, i_gemm = 0, i_dw = 0, it0;
+      long long iw_ready = 0, iw_full = 0, iw_peer = 0, iw_rb = 0, i_gemm = 0, i_dw = 0, iw_full_g = 0, iw_peer_g = 0;
 #define ITM(acc, stmt) { const long long a_ = clock64(); stmt; acc += clock64() - a_; }
 #else
 #define ITM(acc, stmt) stmt;
@@ -413,17 +397,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       auto gemm_k = [&]() {
 #pragma unroll
         for (int c = 0; c < TC_WCHUNKS; ++c) {
-          const int s = c % TC_STAGES;
-          ITM(iw_full, mbar_wait(&full[s], rp))
-          ITM(iw_peer, mbar_wait(&full_peer[s], rp))
+          const uint32_t s = rs;
+          ITM(iw_full_g, mbar_wait(&full[s], rp))
+          ITM(iw_peer_g, mbar_wait(&full_peer[s], rp))
+          const uint64_t bd = bd_k + (uint64_t)(s * (uint32_t)STG);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const int kstep = c * 4 + kk;  // 8 contraction features per MMA = two 16-byte K chunks
-            umma_tf32(tmem_base, ad_op + (uint64_t)(kstep * (2 * OP_LBO / 16)),
-                      bd_k + (uint64_t)s * STG + (uint64_t)(kk * (2 * (TC_H / 2) * 16 / 16)), idesc_k, kstep > 0 ? 1u : 0u);
+            umma_tf32(tmem_base, ad_op + (uint64_t)(kstep * (2 * OP_LBO / 16)), bd + (uint64_t)(kk * (2 * (TC_H / 2) * 16 / 16)),
+                      idesc_k, kstep > 0 ? 1u : 0u);
           }
           umma_commit(&empty[s]);
-          if (s == TC_STAGES - 1) rp ^= 1u;
+          if (++rs == TC_STAGES) rs = 0, rp ^= 1u;
         }
         umma_commit(mma_done);
       };
@@ -443,15 +428,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             ++nB;
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
-              const int s = q % TC_STAGES;
+              const uint32_t s = rs;
               ITM(iw_full, mbar_wait(&full[s], rp))
               ITM(iw_peer, mbar_wait(&full_peer[s], rp))
+              const uint64_t dd = d_mn + (uint64_t)(s * (uint32_t)STG);
 #pragma unroll
               for (int kk = 0; kk < 2; ++kk)
-                umma_tf32(tmem_base + 256u, d_mn + (uint64_t)s * STG + (uint64_t)(kk * 64),
-                          d_mn + (uint64_t)s * STG + (uint64_t)(512 + kk * 64), idesc_mn, (q > 0 || kk > 0) ? 1u : 0u);
+                umma_tf32(tmem_base + 256u, dd + (uint64_t)(kk * 64), dd + (uint64_t)(512 + kk * 64), idesc_mn,
+                          (q > 0 || kk > 0) ? 1u : 0u);
               umma_commit(&empty[s]);
-              if (s == TC_STAGES - 1) rp ^= 1u;
+              if (++rs == TC_STAGES) rs = 0, rp ^= 1u;
             }
             umma_commit(mma_done_b);
           };
@@ -464,8 +450,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       }
 #ifdef PINN_TC_DEBUG
       if (blockIdx.x == 0)
-        printf("TC issuer (cycles per tile pair): wait op_ready %lld | gemm jobs %lld (14) | dW jobs %lld (7) | of which wait full %lld, wait peer %lld, wait rb_free %lld\n",
-               iw_ready / my_tiles, i_gemm / my_tiles, i_dw / my_tiles, iw_full / my_tiles, iw_peer / my_tiles, iw_rb / my_tiles);
+        printf("TC issuer (cycles per tile pair): wait op_ready %lld | fwd+adj jobs %lld (14) | dW jobs %lld (7) | gemm waits: full %lld, peer %lld | dW waits: full %lld, peer %lld, rb_free %lld\n",
+               iw_ready / my_tiles, i_gemm / my_tiles, i_dw / my_tiles, iw_full_g / my_tiles, iw_peer_g / my_tiles, iw_full / my_tiles, iw_peer / my_tiles, iw_rb / my_tiles);
 #endif
     }
   } else {
@@ -480,10 +466,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     // this thread's features in block b (16 columns): f = cbase + 16 b + 8 u + 2 cq + e, u, e in {0, 1}
     // operand image: element (jet j, block b, u, e) at op_thr + ((cbase + 16 b)/4 + 2u) * OP_LBO + j * 128 + e * 4
     unsigned char* op_thr = op + (cbase / 4 + (cq >> 1)) * OP_LBO + mrow0 * 16 + (cq & 1) * 8;
-    // P-image: element (j, b, u, e) at float  img_thr + (j>>1)*4096 + (j&1)*256 + (b>>1)*512 + ((2(b&1)+u) ^ (pp&3))*8 + e
-    const int img_thr = (2 * sp) * TC_STAGE_FLOATS + (2 * half) * 512 + pp * 32 + cq * 2;
+    // G image (Zbar part; the a part is TC_STAGE_FLOATS / 2 floats further): element (j, b, u, e) at float
+    //   img_thr + (j>>1)*8192 + (j&1)*256 + (b>>1)*512 + ((2(b&1)+u) ^ (pp&3))*8 + e
+    const int img_thr = (2 * sp) * (2 * TC_STAGE_FLOATS) + (half >> 1) * TC_STAGE_FLOATS + (2 * (half & 1)) * 512 + pp * 32 + cq * 2;
+    constexpr int IMG_A = TC_STAGE_FLOATS / 2;   // offset of the a_{l-1} part inside a 16 KB piece
     auto img_off = [&](int j, int b, int u) {
-      return img_thr + (j >> 1) * TC_STAGE_FLOATS + (j & 1) * 256 + (b >> 1) * 512 + (((2 * (b & 1) + u) ^ (pp & 3)) << 3);
+      return img_thr + (j >> 1) * (2 * TC_STAGE_FLOATS) + (j & 1) * 256 + (b >> 1) * 512 + (((2 * (b & 1) + u) ^ (pp & 3)) << 3);
     };
     int nzs = 0;  // Zbar spills published
     int mj = 0;   // adjoint / forward MMA jobs waited for
@@ -624,8 +612,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int f = cbase + 16 * b + 8 * (i >> 1) + 2 * cq + (i & 1);
-            const float4 wa = *reinterpret_cast<const float4*>(w0s + f * 8);
-            const float4 wb = *reinterpret_cast<const float4*>(w0s + f * 8 + 4);
+            const float4 wa = __ldg(reinterpret_cast<const float4*>(w0p + f * 8));
+            const float4 wb = __ldg(reinterpret_cast<const float4*>(w0p + f * 8 + 4));
             const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
             float acc = __ldg(b0 + f);
 #pragma unroll
@@ -644,7 +632,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           }
           activate(z);
           st_op_block(b, z);
-          if (BWD && NHH >= 1) st_img_block(slab, b, z);
+          if (BWD && NHH >= 1) st_img_block(slab + IMG_A, b, z);
         }
       }
       TCT(1)
@@ -659,7 +647,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           for (int i = 0; i < 4; ++i) bl[b][i] = __ldg(bias_l + 16 * b + 8 * (i >> 1) + (i & 1));
         wait_mma();
         TCT(2)
-        float* img = slab + (size_t)l * TC_IMG;
+        float* img = slab + (size_t)l * TC_GIMG + IMG_A;
         const bool spill = BWD && l <= L - 3;
 #pragma unroll
         for (int b = 0; b < TC_NBLK; ++b) {
@@ -689,7 +677,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           const float4 a = *reinterpret_cast<const float4*>(op + q * OP_LBO + mm * 16);
 #pragma unroll
           for (int ci = 0; ci < NCI; ++ci) {
-            const float4 w = *reinterpret_cast<const float4*>(wls + (cs + NCS * ci) * TC_H + 4 * q);
+            const float4 w = __ldg(reinterpret_cast<const float4*>(wlp + (cs + NCS * ci) * TC_H + 4 * q));
             acc[ci] = fmaf(a.x, w.x, fmaf(a.y, w.y, fmaf(a.z, w.z, fmaf(a.w, w.w, acc[ci]))));
           }
         }
@@ -758,7 +746,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           zl[j][0] = t0.x, zl[j][1] = t0.y, zl[j][2] = t0.z, zl[j][3] = t0.w;
           zl[j][4] = t1.x, zl[j][5] = t1.y, zl[j][6] = t1.z, zl[j][7] = t1.w;
         }
-        float* zdst = zimg + (size_t)((L - 2) % TC_ZBUFS) * TC_IMG;
+        float* zdst = slab + (size_t)(L - 3) * TC_GIMG;
         float* dbl = db_s + (size_t)(L - 3) * TC_H;
         for (int b = 0; b < TC_NBLK; ++b) {
           float ab[4][4], act[4][4];
@@ -770,7 +758,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           for (int c = 0; c < 8; ++c) {
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-              const float2 w = *reinterpret_cast<const float2*>(wls + c * TC_H + cbase + 16 * b + 8 * u + 2 * cq);
+              const float2 w = __ldg(reinterpret_cast<const float2*>(wlp + c * TC_H + cbase + 16 * b + 8 * u + 2 * cq));
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 ab[j][2 * u] = fmaf(zl[j][c], w.x, ab[j][2 * u]);
@@ -822,8 +810,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       for (int l = L - 2; l >= 1; --l) {
         // adjoint through the activation of layer l-1 -> Zbar_{l-1} in place (+ spill for its weight gradient)
         {
-          const float* aimg = slab + (size_t)(l - 1) * TC_IMG;
-          float* zdst = zimg + (size_t)((l - 1) % TC_ZBUFS) * TC_IMG;
+          const float* aimg = slab + (size_t)(l - 1) * TC_GIMG + IMG_A;
+          float* zdst = slab + (size_t)(l >= 2 ? l - 2 : 0) * TC_GIMG;
           float* dbl = db_s + (size_t)(l >= 2 ? l - 2 : 0) * TC_H;
           const bool hidden = l > 1;
           float act[TC_NBLK][4][4];
@@ -936,11 +924,23 @@ __global__ void pack_tc_kernel(const __grid_constant__ pinn_desc_t D, const floa
     fwd[at(n, k)] = w;
     adj[at(k, n)] = w;
   }
+  if (hl == 0) {   // zero-padded copies of the two edge layers (read with __ldg by every CTA)
+    const int L = D.n_linear, o = D.widths[L];
+    const long long poffL = (long long)d * TC_H + TC_H + (long long)(L - 2) * ((long long)TC_H * TC_H + TC_H);
+    float* w0p = packed + (size_t)(L - 2) * 2 * TC_H * TC_H;
+    float* wlp = w0p + TC_H * 8;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < TC_H * 8; i += gridDim.x * blockDim.x) {
+      const int f = i >> 3, c = i & 7;
+      w0p[i] = c < d ? params[(long long)f * d + c] : 0.f;
+      const int c2 = i / TC_H, f2 = i - c2 * TC_H;
+      wlp[i] = c2 < o ? params[poffL + (long long)c2 * TC_H + f2] : 0.f;
+    }
+  }
 }
 
 // --------------------------------------------------------------------------------------- host side
 constexpr size_t tc_smem_bytes() {
-  return (size_t)OP_BYTES + (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)TC_H * 8 * 4 + (size_t)8 * TC_H * 4 +
+  return (size_t)OP_BYTES + (size_t)TC_STAGES * TC_STAGE_BYTES +
          (size_t)TC_M * 8 * 4 + (size_t)TC_TP * 8 * 4 + (size_t)TC_MAX_HH * TC_H * 4 + PINN_NSUMS * 8 + (3 * TC_STAGES + 7) * 8 + 16;
 }
 
@@ -967,8 +967,8 @@ int tc_workspace(const pinn_desc_t* D, long long n_points, int sms, size_t* pack
   if (pairs < 1) pairs = 1;
   long long g = 2 * pairs;   // CTA pairs (clusters of 2)
   *grid = (int)g;
-  *packed_bytes = (size_t)(L - 2) * 2 * TC_H * TC_H * 4;
-  *slab_stride = (long long)((L - 2) + TC_ZBUFS) * TC_IMG;   // P-images of (L-2) layer outputs + the Zbar spills in flight
+  *packed_bytes = (size_t)(L - 2) * 2 * TC_H * TC_H * 4 + (size_t)2 * TC_H * 8 * 4;   // + padded edge layers
+  *slab_stride = (long long)(L - 2) * TC_GIMG;   // one weight-gradient operand image per hidden layer
   *slab_bytes = (size_t)g * (size_t)(*slab_stride) * 4;
   return PINN_OK;
 }
