@@ -25,8 +25,8 @@
 //   warp  17   MMA issuer: one thread issues tcgen05.mma and tcgen05.commit; owns the TMEM allocation
 //
 // Operand image in shared memory (K-major, no swizzle): element (row m, feature f) at byte
-//   (f/4)*OP_LBO + m*16 + (f%4)*4, OP_LBO = 128*16 + 64: the canonical K-major UMMA layout with
-//   LBO = OP_LBO, SBO = 128; the 64-byte pad makes the 8-byte jets-in-thread accesses conflict-free.
+//   (f/4)*OP_LBO + m*16 + (f%4)*4, OP_LBO = 128*16 + 32: the canonical K-major UMMA layout with
+//   LBO = OP_LBO, SBO = 128; the 32-byte pad makes the 16-byte jets-in-thread accesses conflict-free.
 // Spill image in global memory (G_l, 256 KB per hidden layer l per tile) = the two operands of the weight-gradient
 //   job of layer l, Zbar_l (written in the reverse sweep) and a_{l-1} (written in the forward sweep), in 16-row chunks
 //   of 32 KB: [feature half 0: Zbar 8 KB | a 8 KB][feature half 1: Zbar 8 KB | a 8 KB], each 8 KB piece =
@@ -53,7 +53,7 @@ constexpr int TC_PARTS = TC_WORKERS / TC_H;  // worker threads per feature in th
 constexpr int TC_STAGES = 5;
 constexpr int TC_STAGE_BYTES = 16384;
 constexpr int TC_STAGE_FLOATS = TC_STAGE_BYTES / 4;
-constexpr int OP_LBO = TC_M * 16 + 64;     // 2112
+constexpr int OP_LBO = TC_M * 16 + 32;     // 2080
 constexpr int OP_BYTES = (TC_H / 4) * OP_LBO;
 constexpr int TC_IMG = TC_M * TC_H;        // floats per spill image (one quantity of one layer of one tile)
 constexpr int TC_GIMG = 2 * TC_IMG;        // floats per weight-gradient operand image (Zbar_l and a_{l-1} interleaved)
@@ -217,12 +217,12 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return umma_desc(smem_addr, lbo_bytes, sbo_bytes) | ((uint64_t)1 << 61);
 }
-__device__ __forceinline__ void st_global_v2(float* p, float a, float b) {
-  asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+__device__ __forceinline__ void st_global_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-__device__ __forceinline__ float2 ld_global_v2(const float* p) {
-  float2 v;
-  asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+__device__ __forceinline__ float4 ld_global_v4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
   return v;
 }
 
@@ -463,15 +463,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     const int mrow0 = sp * 32 + pp;              // row of its value jet; jet j sits at row mrow0 + 8 j
     const uint32_t tmem_sp = tmem_base + ((uint32_t)(sp * 32) << 16);
     const float inv_cnt = (kind == PINN_RES_CONT_ONLY && A.mask_count) ? 1.0f / *A.mask_count : 0.f;
-    // this thread's features in block b (16 columns): f = cbase + 16 b + 8 u + 2 cq + e, u, e in {0, 1}
-    // operand image: element (jet j, block b, u, e) at op_thr + ((cbase + 16 b)/4 + 2u) * OP_LBO + j * 128 + e * 4
-    unsigned char* op_thr = op + (cbase / 4 + (cq >> 1)) * OP_LBO + mrow0 * 16 + (cq & 1) * 8;
-    // G image (Zbar part; the a part is TC_STAGE_FLOATS / 2 floats further): element (j, b, u, e) at float
-    //   img_thr + (j>>1)*8192 + (j&1)*256 + (b>>1)*512 + ((2(b&1)+u) ^ (pp&3))*8 + e
-    const int img_thr = (2 * sp) * (2 * TC_STAGE_FLOATS) + (half >> 1) * TC_STAGE_FLOATS + (2 * (half & 1)) * 512 + pp * 32 + cq * 2;
+    // This thread's features in block b (16 columns).  The rows of the weight images are permuted inside every group
+    // of 16 (pack_tc_kernel) so that MMA column 16 b + 8 u + 2 cq + e holds feature 16 b + 4 cq + 2 u + e: the four
+    // values a thread gets from a 16x256b.x2 load, v[j][i = 2u+e], are the FOUR CONSECUTIVE features
+    //   f = cbase + 16 b + 4 cq + i
+    // i.e. one 16-byte unit of the operand image and of the spill image (128-bit shared / global accesses).
+    // operand image: (jet j, block b) at op_thr + 4 b * OP_LBO + j * 128
+    unsigned char* op_thr = op + (cbase / 4 + cq) * OP_LBO + mrow0 * 16;
+    // G image (Zbar part; the a part is TC_STAGE_FLOATS / 2 floats further): (j, b) at float
+    //   img_thr + (j>>1)*8192 + (j&1)*256 + (b>>1)*512 + ((2(b&1) + cq/2) ^ (pp&3))*8
+    const int img_thr = (2 * sp) * (2 * TC_STAGE_FLOATS) + (half >> 1) * TC_STAGE_FLOATS + (2 * (half & 1)) * 512 + pp * 32 + (cq & 1) * 4;
     constexpr int IMG_A = TC_STAGE_FLOATS / 2;   // offset of the a_{l-1} part inside a 16 KB piece
-    auto img_off = [&](int j, int b, int u) {
-      return img_thr + (j >> 1) * (2 * TC_STAGE_FLOATS) + (j & 1) * 256 + (b >> 1) * 512 + (((2 * (b & 1) + u) ^ (pp & 3)) << 3);
+    auto img_off = [&](int j, int b) {
+      return img_thr + (j >> 1) * (2 * TC_STAGE_FLOATS) + (j & 1) * 256 + (b >> 1) * 512 + (((2 * (b & 1) + (cq >> 1)) ^ (pp & 3)) << 3);
     };
     int nzs = 0;  // Zbar spills published
     int mj = 0;   // adjoint / forward MMA jobs waited for
@@ -520,34 +524,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     };
     auto st_op_block = [&](int b, const float (&v)[4][4]) {
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<float2*>(op_thr + (4 * b + 2 * u) * OP_LBO + j * 128) = make_float2(v[j][2 * u], v[j][2 * u + 1]);
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<float4*>(op_thr + 4 * b * OP_LBO + j * 128) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
     };
     auto ld_op_block = [&](int b, float (&v)[4][4]) {
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 t = *reinterpret_cast<const float2*>(op_thr + (4 * b + 2 * u) * OP_LBO + j * 128);
-          v[j][2 * u] = t.x, v[j][2 * u + 1] = t.y;
-        }
+      for (int j = 0; j < 4; ++j) {
+        const float4 t = *reinterpret_cast<const float4*>(op_thr + 4 * b * OP_LBO + j * 128);
+        v[j][0] = t.x, v[j][1] = t.y, v[j][2] = t.z, v[j][3] = t.w;
+      }
     };
     auto st_img_block = [&](float* img, int b, const float (&v)[4][4]) {
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) st_global_v2(img + img_off(j, b, u), v[j][2 * u], v[j][2 * u + 1]);
+      for (int j = 0; j < 4; ++j) st_global_v4(img + img_off(j, b), v[j][0], v[j][1], v[j][2], v[j][3]);
     };
     auto ld_img_block = [&](const float* img, int b, float (&v)[4][4]) {
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 t = ld_global_v2(img + img_off(j, b, u));
-          v[j][2 * u] = t.x, v[j][2 * u + 1] = t.y;
-        }
+      for (int j = 0; j < 4; ++j) {
+        const float4 t = ld_global_v4(img + img_off(j, b));
+        v[j][0] = t.x, v[j][1] = t.y, v[j][2] = t.z, v[j][3] = t.w;
+      }
     };
     // forward activation: pre-activation jets z (value row already carries the bias) -> post-activation jets
     auto activate = [&](float (&z)[4][4]) {
@@ -588,7 +584,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       const float s = b3 ? k0 : k1;
       k += __shfl_xor_sync(0xffffffffu, s, 8);      // holds u = b4, e = b3
       k += __shfl_xor_sync(0xffffffffu, k, 4);
-      if (!(lane & 4)) atomicAdd(dbl + cbase + 16 * b + 8 * (b4 ? 1 : 0) + 2 * cq + (b3 ? 1 : 0), k);
+      if (!(lane & 4)) atomicAdd(dbl + cbase + 16 * b + 4 * cq + 2 * (b4 ? 1 : 0) + (b3 ? 1 : 0), k);
     };
 
     for (int it = 0; it < my_tiles; ++it) {
@@ -611,7 +607,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           float z[4][4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int f = cbase + 16 * b + 8 * (i >> 1) + 2 * cq + (i & 1);
+            const int f = cbase + 16 * b + 4 * cq + i;
             const float4 wa = __ldg(reinterpret_cast<const float4*>(w0p + f * 8));
             const float4 wb = __ldg(reinterpret_cast<const float4*>(w0p + f * 8 + 4));
             const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
@@ -639,12 +635,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       signal_ready();
       // ---------------- hidden layers 1..L-2 on the tensor cores ----------------
       for (int l = 1; l <= L - 2; ++l) {
-        const float* bias_l = A.params + P0 + (long long)(l - 1) * PH + (long long)TC_H * TC_H + cbase + 2 * cq;
+        const float* bias_l = A.params + P0 + (long long)(l - 1) * PH + (long long)TC_H * TC_H + cbase + 4 * cq;
         float bl[TC_NBLK][4];
 #pragma unroll
         for (int b = 0; b < TC_NBLK; ++b)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) bl[b][i] = __ldg(bias_l + 16 * b + 8 * (i >> 1) + (i & 1));
+          for (int i = 0; i < 4; ++i) bl[b][i] = __ldg(bias_l + 16 * b + i);
         wait_mma();
         TCT(2)
         float* img = slab + (size_t)l * TC_GIMG + IMG_A;
@@ -756,14 +752,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             for (int i = 0; i < 4; ++i) ab[j][i] = 0.f;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(wlp + c * TC_H + cbase + 16 * b + 4 * cq));
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const float2 w = __ldg(reinterpret_cast<const float2*>(wlp + c * TC_H + cbase + 16 * b + 8 * u + 2 * cq));
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                ab[j][2 * u] = fmaf(zl[j][c], w.x, ab[j][2 * u]);
-                ab[j][2 * u + 1] = fmaf(zl[j][c], w.y, ab[j][2 * u + 1]);
-              }
+            for (int j = 0; j < 4; ++j) {
+              ab[j][0] = fmaf(zl[j][c], w.x, ab[j][0]);
+              ab[j][1] = fmaf(zl[j][c], w.y, ab[j][1]);
+              ab[j][2] = fmaf(zl[j][c], w.z, ab[j][2]);
+              ab[j][3] = fmaf(zl[j][c], w.w, ab[j][3]);
             }
           }
           ld_op_block(b, act);
@@ -913,8 +908,10 @@ __global__ void pack_tc_kernel(const __grid_constant__ pinn_desc_t D, const floa
   float* fwd = packed + (size_t)hl * 2 * TC_H * TC_H;
   float* adj = fwd + (size_t)TC_H * TC_H;
   auto at = [](int n, int k) {   // float offset of B[n][k] inside its direction's two half-images
-    return (size_t)(n >> 7) * (TC_H * TC_H / 2) + (size_t)(k >> 5) * TC_STAGE_FLOATS + (size_t)((k & 31) >> 2) * 512 +
-           (size_t)(n & 127) * 4 + (size_t)(k & 3);
+    // feature n = 16 g + 4 cq + 2 u + e sits in MMA row 16 g + 8 u + 2 cq + e (see the worker addressing)
+    const int nr = (n & ~15) | (((n >> 1) & 1) << 3) | (((n >> 2) & 3) << 1) | (n & 1);
+    return (size_t)(nr >> 7) * (TC_H * TC_H / 2) + (size_t)(k >> 5) * TC_STAGE_FLOATS + (size_t)((k & 31) >> 2) * 512 +
+           (size_t)(nr & 127) * 4 + (size_t)(k & 3);
   };
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < TC_H * TC_H; i += gridDim.x * blockDim.x) {
     const int n = i / TC_H, k = i - n * TC_H;
