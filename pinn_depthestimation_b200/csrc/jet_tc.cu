@@ -56,6 +56,11 @@ constexpr int TC_STAGE_FLOATS = TC_STAGE_BYTES / 4;
 constexpr int OP_LBO = TC_M * 16 + 32;     // 2080
 constexpr int OP_BYTES = (TC_H / 4) * OP_LBO;
 constexpr int TC_IMG = TC_M * TC_H;        // floats per spill image (one quantity of one layer of one tile)
+constexpr int TC_EDGE_W0 = 0;               // float offsets inside the edge block that follows the hidden-layer weight images
+constexpr int TC_EDGE_WL = TC_H * 8;        //   W0 padded [H][8] | Wlast padded [8][H] | forward-last B images [2][4096] | reverse-last B images [2][1024]
+constexpr int TC_EDGE_E1 = 2 * TC_H * 8;
+constexpr int TC_EDGE_E2 = TC_EDGE_E1 + 2 * TC_STAGE_FLOATS;
+constexpr int TC_EDGE_FLOATS = TC_EDGE_E2 + 2 * 1024;
 constexpr int TC_GIMG = 2 * TC_IMG;        // floats per weight-gradient operand image (Zbar_l and a_{l-1} interleaved)
 constexpr int TC_WCHUNKS = TC_H * (TC_H / 2) * 4 / TC_STAGE_BYTES;   // 8 chunks per half-width weight image
 constexpr int TC_MAX_HH = 7;               // hidden->hidden layers whose bias gradients are staged in shared memory
@@ -211,6 +216,16 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2_nowait(uint32_t taddr, uint32
                : "r"(taddr)
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, float (&v)[8]) {   // thread = TMEM lane, 8 columns
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // MN-major operand descriptor, SWIZZLE_128B_BASE32B (layout type 1): LBO = stride between 32-element
 // panels along M/N, SBO = stride between 4-row atoms along K
@@ -226,13 +241,16 @@ __device__ __forceinline__ float4 ld_global_v4(const float* p) {
   return v;
 }
 
-struct TileJets {  // output jets of one point in the [128 rows][8] area, row = 32*(p/8) + 8*j + p%8
+// Output jets / adjoint seeds of a tile live in a K-major UMMA operand image [k/4 (2)][row (128)][4] (the A operand of
+// the reverse last-layer MMA): element (row m, output column c) at float (c/4)*512 + m*4 + c%4.
+__device__ __forceinline__ int outs_idx(int m, int c) { return (c >> 2) * 512 + m * 4 + (c & 3); }
+struct TileJets {  // output jets of one point, row = 32*(p/8) + 8*j + p%8
   float* outs;
   int p;
   __device__ __forceinline__ int row(int j) const { return 32 * (p >> 3) + 8 * j + (p & 7); }
-  __device__ __forceinline__ float get(int col, int j) const { return outs[row(j) * 8 + col]; }
-  __device__ __forceinline__ void set(int col, int j, float v) { outs[row(j) * 8 + col] = v; }
-  __device__ __forceinline__ void add(int col, int j, float v) { outs[row(j) * 8 + col] += v; }
+  __device__ __forceinline__ float get(int col, int j) const { return outs[outs_idx(row(j), col)]; }
+  __device__ __forceinline__ void set(int col, int j, float v) { outs[outs_idx(row(j), col)] = v; }
+  __device__ __forceinline__ void add(int col, int j, float v) { outs[outs_idx(row(j), col)] += v; }
 };
 
 #ifdef PINN_TC_DEBUG
@@ -284,8 +302,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   const long long P0 = (long long)d * TC_H + TC_H;               // params of layer 0
   const long long PH = (long long)TC_H * TC_H + TC_H;            // params of a hidden->hidden layer
   const long long poffL = P0 + (long long)NHH * PH;              // params offset of the last layer
-  const float* w0p = A.packed + (size_t)NHH * 2 * TC_H * TC_H;   // [H][8]  W0[f][c], zero-padded (L1-resident)
-  const float* wlp = w0p + TC_H * 8;                             // [8][H]  Wlast[c][f], zero-padded
+  const float* edge = A.packed + (size_t)NHH * 2 * TC_H * TC_H;  // edge-layer block of the packed weights
+  const float* w0p = edge + TC_EDGE_W0;                          // [H][8]  W0[f][c], zero-padded (L1-resident)
 
   // ---------------- one-time setup ----------------
   if (tid == 0) {
@@ -325,18 +343,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     if (lane == 0) {
       int ps = 0, nzt = 0;
       uint32_t pph = 1;     // parity to wait for on empty[ps] (first pass: fresh barriers count as released)
-      auto load = [&](const float* src) {
+      auto load_n = [&](const float* src, uint32_t bytes) {
         mbar_wait(&empty[ps], pph);
-        mbar_expect_tx(&full[ps], TC_STAGE_BYTES);
-        tma_load_1d(ring + ps * TC_STAGE_BYTES, src, TC_STAGE_BYTES, &full[ps]);
+        mbar_expect_tx(&full[ps], bytes);
+        tma_load_1d(ring + ps * TC_STAGE_BYTES, src, bytes, &full[ps]);
         if (++ps == TC_STAGES) ps = 0, pph ^= 1u;
       };
+      auto load = [&](const float* src) { load_n(src, TC_STAGE_BYTES); };
       const size_t half_off = (size_t)rank * (TC_H * TC_H / 2);
       for (int it = 0; it < my_tiles; ++it) {
         for (int hl = 0; hl < NHH; ++hl)
           for (int c = 0; c < TC_WCHUNKS; ++c)
             load(A.packed + (size_t)hl * 2 * TC_H * TC_H + half_off + (size_t)c * TC_STAGE_FLOATS);
+        load(edge + TC_EDGE_E1 + (size_t)rank * TC_STAGE_FLOATS);   // last layer, forward: 256 x 16 B image of this CTA
         if (BWD) {
+          load_n(edge + TC_EDGE_E2 + (size_t)rank * 1024, 4096);    // last layer, reverse: 8 x 128 B image of this CTA
           mbar_wait(slab_ready, (uint32_t)(it & 1));  // both tiles' activation spills are written and fenced
           for (int l = L - 2; l >= 1; --l) {
             for (int c = 0; c < TC_WCHUNKS; ++c)       // adjoint job of layer l
@@ -357,7 +378,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     if (lane < TC_STAGES && rank != 0) {
       // follower: relay "my stage has landed" to the leader's issuer (1-D bulk copies cannot signal a peer barrier);
       // one lane per ring stage so the hand-offs of different stages overlap
-      const int per_tile = NHH * TC_WCHUNKS + (BWD ? NHH * (TC_WCHUNKS + 16) : 0);
+      const int per_tile = NHH * TC_WCHUNKS + 1 + (BWD ? 1 + NHH * (TC_WCHUNKS + 16) : 0);
       const long long total = (long long)my_tiles * per_tile;
       const long long passes = (total - lane + TC_STAGES - 1) / TC_STAGES;
       const uint32_t fp = mapa_u32(&full_peer[lane], 0);
@@ -371,6 +392,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc_k = umma_idesc(2 * TC_M, TC_H, 0, 0);
       constexpr uint32_t idesc_mn = umma_idesc(2 * TC_M, TC_H, 1, 1);
+      constexpr uint32_t idesc_last = umma_idesc(2 * TC_M, 32, 0, 0);   // 256 -> o forward: N = 2 x 16 (zero-padded)
       // The issue loop runs on ONE thread: every scalar instruction in it is on the tensor pipe's critical path
       // (a 128x256x8 TF32 MMA retires in ~130 cycles, tools/mma_rate_probe.cu).  Descriptors are therefore
       // built once; per MMA only the 14-bit start-address field (16-byte units) advances by a compile-time
@@ -378,6 +400,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       const uint64_t ad_op = umma_desc(smem_u32(op), OP_LBO, 128);            // + kstep * (2 * OP_LBO / 16)
       const uint64_t bd_k = umma_desc(smem_u32(ring), (TC_H / 2) * 16, 128);  // K-major half-width weight chunk in stage 0
       const uint64_t d_mn = umma_desc_mn(smem_u32(ring), 2048, 512);          // MN-major spill half-chunk in stage 0
+      const uint64_t bd_last = umma_desc(smem_u32(ring), 16 * 16, 128);       // [k/4][16 rows][4] last-layer image in stage 0
+      const uint64_t bd_rl = umma_desc(smem_u32(ring), (TC_H / 2) * 16, 128); // [2][128 rows][4] reverse last-layer image
+      const uint64_t ad_outs = umma_desc(smem_u32(outs), TC_M * 16, 128);     // [2][128 rows][4] adjoint seeds (K = 8 outputs)
       constexpr uint64_t STG = TC_STAGE_BYTES / 16;
       uint32_t rp = 0;      // parity of the ring pass (flips every TC_STAGES chunks)
       uint32_t rs = 0;      // ring stage of the next chunk
@@ -417,7 +442,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           wait_ready();
           ITM(i_gemm, gemm_k())
         }
+        {
+          // last layer forward: D[256 x 32] = OP * Wlast^T (columns >= o are zero), one ring stage
+          wait_ready();
+          const uint32_t s = rs;
+          ITM(iw_full_g, mbar_wait(&full[s], rp))
+          ITM(iw_peer_g, mbar_wait(&full_peer[s], rp))
+          const uint64_t bd = bd_last + (uint64_t)(s * (uint32_t)STG);
+#pragma unroll
+          for (int kstep = 0; kstep < TC_H / 8; ++kstep)
+            umma_tf32(tmem_base, ad_op + (uint64_t)(kstep * (2 * OP_LBO / 16)), bd + (uint64_t)(kstep * (2 * 16 * 16 / 16)), idesc_last,
+                      kstep > 0 ? 1u : 0u);
+          umma_commit(&empty[s]);
+          if (++rs == TC_STAGES) rs = 0, rp ^= 1u;
+          umma_commit(mma_done);
+        }
         if (BWD) {
+          {
+            // last layer reverse: Abar_{L-2}[256 x 256] = seeds[256 x 8] * Wlast: ONE MMA (K = 8)
+            wait_ready();
+            const uint32_t s = rs;
+            ITM(iw_full_g, mbar_wait(&full[s], rp))
+            ITM(iw_peer_g, mbar_wait(&full_peer[s], rp))
+            umma_tf32(tmem_base, ad_outs, bd_rl + (uint64_t)(s * (uint32_t)STG), idesc_k, 0u);
+            umma_commit(&empty[s]);
+            if (++rs == TC_STAGES) rs = 0, rp ^= 1u;
+            umma_commit(mma_done);
+          }
           // weight-gradient job of one layer into TMEM columns 256..511: both operands MN-major (contraction over
           // the 2 x 128 rows of the pair's tiles); per stage = 16 rows: [Zbar half-chunk 8 KB][A_in half-chunk 8 KB]
           auto dw_job = [&]() {
@@ -656,36 +707,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           if (spill) st_img_block(img, b, z);
         }
         TCT(1)
-        if (l < L - 2) signal_ready();
+        signal_ready();   // next hidden layer, or (after the last one) the 256 -> o job
       }
       if (BWD) publish_spill(slab_ready);
+      TCT(3)
+      // ---------------- last layer (256 -> o): tensor-core job with N = 32, read back thread-per-row ----------------
+      wait_mma();
+      if (half == 0) {
+        const int mm = sp * 32 + lane;   // this thread's TMEM lane = tile row
+        float v[8];
+        tmem_ld_32x32b_x8(tmem_sp, v);
+        if (((mm >> 3) & 3) == 0) {      // value rows carry the bias
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (c < o) v[c] += __ldg(A.params + poffL + (long long)TC_H * o + c);
+        }
+        *reinterpret_cast<float4*>(outs + mm * 4) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(outs + 512 + mm * 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
       tc_fence_before();
       worker_bar();
-      TCT(3)
-      // ---------------- last layer (256 -> o) on the FP32 pipes ----------------
-      {
-        constexpr int NCS = TC_WORKERS / 128, NCI = 8 / NCS;
-        const int mm = tid & 127, cs = tid >> 7;
-        float acc[NCI];
-#pragma unroll
-        for (int ci = 0; ci < NCI; ++ci) acc[ci] = 0.f;
-        for (int q = 0; q < TC_H / 4; ++q) {
-          const float4 a = *reinterpret_cast<const float4*>(op + q * OP_LBO + mm * 16);
-#pragma unroll
-          for (int ci = 0; ci < NCI; ++ci) {
-            const float4 w = __ldg(reinterpret_cast<const float4*>(wlp + (cs + NCS * ci) * TC_H + 4 * q));
-            acc[ci] = fmaf(a.x, w.x, fmaf(a.y, w.y, fmaf(a.z, w.z, fmaf(a.w, w.w, acc[ci]))));
-          }
-        }
-#pragma unroll
-        for (int ci = 0; ci < NCI; ++ci) {
-          const int c = cs + NCS * ci;
-          float v = acc[ci];
-          if (((mm >> 3) & 3) == 0 && c < o) v += A.params[poffL + (long long)TC_H * o + c];
-          outs[mm * 8 + c] = c < o ? v : 0.f;
-        }
-      }
-      worker_bar();
+      TCT(13)
       // ---------------- residual / misfit epilogue: warp 0, one lane per point ----------------
       if (warp == 0) {
         const long long gp = p0 + lane;
@@ -704,6 +746,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       worker_bar();
       TCT(4)
       if (!BWD) continue;
+      signal_ready();   // the adjoint seeds are in the output image: Abar_{L-2} = seeds * Wlast may start
 
       // =============================== reverse ===============================
       // ---- last layer: dW_last[c][f] = sum_m zbar[m][c] * A[m][f] (thread per feature), db_last ----
@@ -715,8 +758,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         const unsigned char* ap = op + (f >> 2) * OP_LBO + (f & 3) * 4;
         for (int mm = part * (TC_M / TC_PARTS); mm < (part + 1) * (TC_M / TC_PARTS); ++mm) {
           const float a = *reinterpret_cast<const float*>(ap + mm * 16);
-          const float4 z0 = *reinterpret_cast<const float4*>(outs + mm * 8);
-          const float4 z1 = *reinterpret_cast<const float4*>(outs + mm * 8 + 4);
+          const float4 z0 = *reinterpret_cast<const float4*>(outs + mm * 4);
+          const float4 z1 = *reinterpret_cast<const float4*>(outs + 512 + mm * 4);
           acc[0] = fmaf(z0.x, a, acc[0]), acc[1] = fmaf(z0.y, a, acc[1]);
           acc[2] = fmaf(z0.z, a, acc[2]), acc[3] = fmaf(z0.w, a, acc[3]);
           acc[4] = fmaf(z1.x, a, acc[4]), acc[5] = fmaf(z1.y, a, acc[5]);
@@ -727,41 +770,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           if (c < o) atomicAdd(A.grad + poffL + (long long)c * TC_H + f, acc[c]);
         if (tid < o) {
           float s = 0.f;
-          for (int pq = 0; pq < TC_TP; ++pq) s += outs[(32 * (pq >> 3) + (pq & 7)) * 8 + tid];
+          for (int pq = 0; pq < TC_TP; ++pq) s += outs[outs_idx(32 * (pq >> 3) + (pq & 7), tid)];
           atomicAdd(A.grad + poffL + (long long)TC_H * o + tid, s);
         }
       }
       worker_bar();
-      // ---- abar = zbar_last * W_last, through the activation of layer L-2 -> Zbar_{L-2} in place ----
+      TCT(14)
+      // ---- Abar_{L-2} = seeds * W_last (tensor core), through the activation of layer L-2 -> Zbar_{L-2} in place ----
       {
-        float zl[4][8];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 t0 = *reinterpret_cast<const float4*>(outs + (mrow0 + 8 * j) * 8);
-          const float4 t1 = *reinterpret_cast<const float4*>(outs + (mrow0 + 8 * j) * 8 + 4);
-          zl[j][0] = t0.x, zl[j][1] = t0.y, zl[j][2] = t0.z, zl[j][3] = t0.w;
-          zl[j][4] = t1.x, zl[j][5] = t1.y, zl[j][6] = t1.z, zl[j][7] = t1.w;
-        }
         float* zdst = slab + (size_t)(L - 3) * TC_GIMG;
         float* dbl = db_s + (size_t)(L - 3) * TC_H;
+        wait_mma();
+#pragma unroll
         for (int b = 0; b < TC_NBLK; ++b) {
           float ab[4][4], act[4][4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) ab[j][i] = 0.f;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 w = __ldg(reinterpret_cast<const float4*>(wlp + c * TC_H + cbase + 16 * b + 4 * cq));
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              ab[j][0] = fmaf(zl[j][c], w.x, ab[j][0]);
-              ab[j][1] = fmaf(zl[j][c], w.y, ab[j][1]);
-              ab[j][2] = fmaf(zl[j][c], w.z, ab[j][2]);
-              ab[j][3] = fmaf(zl[j][c], w.w, ab[j][3]);
-            }
-          }
           ld_op_block(b, act);
+          ld_block(b, ab);
           adjoint(ab, act);
           st_op_block(b, ab);
           st_img_block(zdst, b, ab);
@@ -878,10 +902,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 #ifdef PINN_TC_DEBUG
     if (blockIdx.x == 0 && tid == 0) {
       long long tot = 0;
-      for (int i = 0; i < 13; ++i) tot += tct[i];
-      printf("TC phases (cycles per tile, %d tiles): in+bar %lld | L0+fwd-epi %lld | fwd-wait-mma %lld | fence+bar %lld | last+residual %lld | rev-last %lld | fence+signal %lld | drain0 %lld | drain1 %lld | wait-adj %lld | adj-epi %lld | L0-rev %lld | total %lld\n", my_tiles,
+      for (int i = 0; i < 15; ++i) tot += tct[i];
+      printf("TC phases (cycles per tile, %d tiles): in+bar %lld | L0+fwd-epi %lld | fwd-wait-mma %lld | fence+bar %lld | last+residual %lld | rev-last %lld | fence+signal %lld | drain0 %lld | drain1 %lld | wait-adj %lld | adj-epi %lld | L0-rev %lld | last-layer %lld | dW_last %lld | total %lld\n", my_tiles,
              tct[0] / my_tiles, tct[1] / my_tiles, tct[2] / my_tiles, tct[3] / my_tiles, tct[4] / my_tiles, tct[5] / my_tiles, tct[6] / my_tiles,
-             tct[7] / my_tiles, tct[8] / my_tiles, tct[9] / my_tiles, tct[10] / my_tiles, tct[12] / my_tiles, tot / my_tiles);
+             tct[7] / my_tiles, tct[8] / my_tiles, tct[9] / my_tiles, tct[10] / my_tiles, tct[12] / my_tiles, tct[13] / my_tiles, tct[14] / my_tiles, tot / my_tiles);
     }
 #endif
   }
@@ -924,13 +948,33 @@ __global__ void pack_tc_kernel(const __grid_constant__ pinn_desc_t D, const floa
   if (hl == 0) {   // zero-padded copies of the two edge layers (read with __ldg by every CTA)
     const int L = D.n_linear, o = D.widths[L];
     const long long poffL = (long long)d * TC_H + TC_H + (long long)(L - 2) * ((long long)TC_H * TC_H + TC_H);
-    float* w0p = packed + (size_t)(L - 2) * 2 * TC_H * TC_H;
-    float* wlp = w0p + TC_H * 8;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < TC_H * 8; i += gridDim.x * blockDim.x) {
-      const int f = i >> 3, c = i & 7;
-      w0p[i] = c < d ? params[(long long)f * d + c] : 0.f;
-      const int c2 = i / TC_H, f2 = i - c2 * TC_H;
-      wlp[i] = c2 < o ? params[poffL + (long long)c2 * TC_H + f2] : 0.f;
+    float* edge = packed + (size_t)(L - 2) * 2 * TC_H * TC_H;
+    float* w0p = edge + TC_EDGE_W0;
+    float* wlp = edge + TC_EDGE_WL;
+    float* e1 = edge + TC_EDGE_E1;   // forward last layer:  rank 0 [k/4 (64)][n (16)][4] = Wlast[n][k], rank 1 zeros
+    float* e2 = edge + TC_EDGE_E2;   // reverse last layer:  rank r [k/4 (2)][n (128)][4] = Wlast[k][128 r + n], rows permuted
+    auto tf32 = [](float x) {
+      uint32_t r;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+      return __uint_as_float(r);
+    };
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * TC_STAGE_FLOATS; i += gridDim.x * blockDim.x) {
+      if (i < TC_H * 8) {
+        const int f = i >> 3, c = i & 7;
+        w0p[i] = c < d ? params[(long long)f * d + c] : 0.f;
+        const int c2 = i / TC_H, f2 = i - c2 * TC_H;
+        wlp[i] = c2 < o ? params[poffL + (long long)c2 * TC_H + f2] : 0.f;
+        // reverse image: i = c2 (k, 0..7) * 256 + f2 (feature)
+        const int n = f2 & 127, nr = (n & ~15) | (((n >> 1) & 1) << 3) | (((n >> 2) & 3) << 1) | (n & 1);
+        e2[(f2 >> 7) * 1024 + (c2 >> 2) * 512 + nr * 4 + (c2 & 3)] = c2 < o ? tf32(params[poffL + (long long)c2 * TC_H + f2]) : 0.f;
+      }
+      // forward image: i < 4096: rank 0, i = k * 16 + n; the rest: rank 1 = zeros
+      if (i < TC_STAGE_FLOATS) {
+        const int k = i >> 4, n = i & 15;
+        e1[(k >> 2) * 64 + n * 4 + (k & 3)] = n < o ? tf32(params[poffL + (long long)n * TC_H + k]) : 0.f;
+      } else {
+        e1[i] = 0.f;
+      }
     }
   }
 }
@@ -964,7 +1008,7 @@ int tc_workspace(const pinn_desc_t* D, long long n_points, int sms, size_t* pack
   if (pairs < 1) pairs = 1;
   long long g = 2 * pairs;   // CTA pairs (clusters of 2)
   *grid = (int)g;
-  *packed_bytes = (size_t)(L - 2) * 2 * TC_H * TC_H * 4 + (size_t)2 * TC_H * 8 * 4;   // + padded edge layers
+  *packed_bytes = (size_t)(L - 2) * 2 * TC_H * TC_H * 4 + (size_t)TC_EDGE_FLOATS * 4;   // + edge-layer block
   *slab_stride = (long long)(L - 2) * TC_GIMG;   // one weight-gradient operand image per hidden layer
   *slab_bytes = (size_t)g * (size_t)(*slab_stride) * 4;
   return PINN_OK;
