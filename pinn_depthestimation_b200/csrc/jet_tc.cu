@@ -275,7 +275,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   uint64_t* empty = full + TC_STAGES;                             // [S]
   uint64_t* full_peer = empty + TC_STAGES;                        // [S] leader only: the follower's stage has landed
   uint64_t* op_ready = full_peer + TC_STAGES;
-  uint64_t* mma_done = op_ready + 1;
+  uint64_t* edge_ready = op_ready + 4;   // op_ready[4]: one barrier per 64-feature slice (a parity-waited barrier must not
+                                         // advance twice unseen, and the workers finish all four slices in a burst);
+                                         // edge_ready: the adjoint seeds are in the output image (not sliced)
+  uint64_t* mma_done = edge_ready + 1;
   uint64_t* slab_ready = mma_done + 1;
   uint64_t* zt_ready = slab_ready + 1;   // [2], alternating per Zbar spill: the workers may run one spill ahead of the
                                          // producer's wait, and a single parity-waited barrier must never advance twice unseen
@@ -313,7 +316,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       mbar_init(&full_peer[s], 1);
     }
     // cross-CTA barriers count one elected arrival per worker warp of each CTA
-    mbar_init(op_ready, 2 * TC_WORKERS / 32);
+    for (int q = 0; q < 4; ++q) mbar_init(&op_ready[q], 2 * TC_WORKERS / 32);
+    mbar_init(edge_ready, 2 * TC_WORKERS / 32);
     mbar_init(mma_done, 1);
     mbar_init(slab_ready, 2 * TC_WORKERS / 32);
     mbar_init(&zt_ready[0], 2 * TC_WORKERS / 32);
@@ -413,15 +417,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 #else
 #define ITM(acc, stmt) stmt;
 #endif
-      auto wait_ready = [&]() {
-        ITM(iw_ready, mbar_wait(op_ready, (uint32_t)(jobs & 1)))
+      // every epilogue hands the operand image over in four 64-feature slices (= two ring stages of K each)
+      auto wait_slice = [&]() {
+        ITM(iw_ready, mbar_wait(&op_ready[jobs & 3], (uint32_t)((jobs >> 2) & 1)))
         ++jobs;
         tc_fence_after();
       };
+      auto wait_ready = [&]() {
+        for (int q = 0; q < 4; ++q) wait_slice();
+      };
+      int nedge = 0;
       // D[256 x 256] = OP (K-major, 256 features; 128 rows in each CTA) * weight half-images (K-major, 128 columns in each CTA)
-      auto gemm_k = [&]() {
+      // into TMEM columns dcol..dcol+255.  PIPELINED: consume the operand image slice by slice as the epilogue of the
+      // previous layer produces it (the accumulator of that layer sits in the OTHER 256 columns, so the epilogue can
+      // still be reading it); otherwise all four slices are awaited first.
+      auto gemm_k = [&](uint32_t dcol, bool pipelined) {
+        if (!pipelined) wait_ready();
 #pragma unroll
         for (int c = 0; c < TC_WCHUNKS; ++c) {
+          if (pipelined && (c & 1) == 0) wait_slice();
           const uint32_t s = rs;
           ITM(iw_full_g, mbar_wait(&full[s], rp))
           ITM(iw_peer_g, mbar_wait(&full_peer[s], rp))
@@ -429,7 +443,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const int kstep = c * 4 + kk;  // 8 contraction features per MMA = two 16-byte K chunks
-            umma_tf32(tmem_base, ad_op + (uint64_t)(kstep * (2 * OP_LBO / 16)), bd + (uint64_t)(kk * (2 * (TC_H / 2) * 16 / 16)),
+            umma_tf32(tmem_base + dcol, ad_op + (uint64_t)(kstep * (2 * OP_LBO / 16)), bd + (uint64_t)(kk * (2 * (TC_H / 2) * 16 / 16)),
                       idesc_k, kstep > 0 ? 1u : 0u);
           }
           umma_commit(&empty[s]);
@@ -439,8 +453,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       };
       for (int it = 0; it < my_tiles; ++it) {
         for (int hl = 0; hl < NHH; ++hl) {
-          wait_ready();
-          ITM(i_gemm, gemm_k())
+          ITM(i_gemm, gemm_k((uint32_t)(((hl + 1) & 1) * 256), true))   // forward job of layer hl+1, accumulator (hl+1) & 1
         }
         {
           // last layer forward: D[256 x 32] = OP * Wlast^T (columns >= o are zero), one ring stage
@@ -460,7 +473,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         if (BWD) {
           {
             // last layer reverse: Abar_{L-2}[256 x 256] = seeds[256 x 8] * Wlast: ONE MMA (K = 8)
-            wait_ready();
+            ITM(iw_ready, mbar_wait(edge_ready, (uint32_t)(nedge & 1)))
+            ++nedge;
+            tc_fence_after();
             const uint32_t s = rs;
             ITM(iw_full_g, mbar_wait(&full[s], rp))
             ITM(iw_peer_g, mbar_wait(&full_peer[s], rp))
@@ -493,8 +508,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             umma_commit(mma_done_b);
           };
           for (int l = L - 2; l >= 1; --l) {
-            wait_ready();                      // Zbar_l is in both operand images, columns 0..255 are drained
-            ITM(i_gemm, gemm_k())              // adjoint of the layer input
+            ITM(i_gemm, gemm_k(0u, false))     // adjoint of the layer input, once Zbar_l is complete in both operand images
             ITM(i_dw, dw_job())                // weight gradient of layer l
           }
         }
@@ -507,26 +521,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     }
   } else {
     // =========================================== workers ============================================
-    const int sp = warp & 3, half = warp >> 2;   // `half` = which TC_WCOLS-wide column slice this warp owns
-    const int cbase = half * TC_WCOLS;
+    const int sp = warp & 3, half = warp >> 2;   // the four warps of a subpartition split every 64-feature slice
+    const int cbase = half * TC_WCOLS;           // (drain only: contiguous column range of this warp)
     const int pp = lane >> 2, cq = lane & 3;     // point within the subpartition, column pair within 8 columns
     const int pt = sp * 8 + pp;                  // this thread's point of the tile
     const int mrow0 = sp * 32 + pp;              // row of its value jet; jet j sits at row mrow0 + 8 j
     const uint32_t tmem_sp = tmem_base + ((uint32_t)(sp * 32) << 16);
     const float inv_cnt = (kind == PINN_RES_CONT_ONLY && A.mask_count) ? 1.0f / *A.mask_count : 0.f;
-    // This thread's features in block b (16 columns).  The rows of the weight images are permuted inside every group
-    // of 16 (pack_tc_kernel) so that MMA column 16 b + 8 u + 2 cq + e holds feature 16 b + 4 cq + 2 u + e: the four
-    // values a thread gets from a 16x256b.x2 load, v[j][i = 2u+e], are the FOUR CONSECUTIVE features
-    //   f = cbase + 16 b + 4 cq + i
-    // i.e. one 16-byte unit of the operand image and of the spill image (128-bit shared / global accesses).
-    // operand image: (jet j, block b) at op_thr + 4 b * OP_LBO + j * 128
-    unsigned char* op_thr = op + (cbase / 4 + cq) * OP_LBO + mrow0 * 16;
+    // This thread's features in block b = slice b of the layer (64 features), 16 of which belong to this warp.  The rows
+    // of the weight images are permuted inside every group of 16 (pack_tc_kernel) so that MMA column 16 g + 8 u + 2 cq + e
+    // holds feature 16 g + 4 cq + 2 u + e: the four values a thread gets from a 16x256b.x2 load, v[j][i = 2u+e], are the
+    // FOUR CONSECUTIVE features
+    //   f = 64 b + 16 half + 4 cq + i
+    // i.e. one 16-byte unit of the operand image and of the spill image (128-bit shared / global accesses).  Slices are
+    // finished by all warps at the same time, so the next layer's MMA can start on slice 0 while slice 1 is computed.
+    // operand image: (jet j, block b) at op_thr + 16 b * OP_LBO + j * 128
+    unsigned char* op_thr = op + (4 * half + cq) * OP_LBO + mrow0 * 16;
     // G image (Zbar part; the a part is TC_STAGE_FLOATS / 2 floats further): (j, b) at float
-    //   img_thr + (j>>1)*8192 + (j&1)*256 + (b>>1)*512 + ((2(b&1) + cq/2) ^ (pp&3))*8
-    const int img_thr = (2 * sp) * (2 * TC_STAGE_FLOATS) + (half >> 1) * TC_STAGE_FLOATS + (2 * (half & 1)) * 512 + pp * 32 + (cq & 1) * 4;
+    //   img_thr + (j>>1)*8192 + (j&1)*256 + (b>>1)*4096 + (2(b&1) + half/2)*512 + ((2(half&1) + cq/2) ^ (pp&3))*8
+    const int img_thr = (2 * sp) * (2 * TC_STAGE_FLOATS) + (half >> 1) * 512 + pp * 32 + (cq & 1) * 4;
+    const int img_swz = 2 * (half & 1) + (cq >> 1);
     constexpr int IMG_A = TC_STAGE_FLOATS / 2;   // offset of the a_{l-1} part inside a 16 KB piece
     auto img_off = [&](int j, int b) {
-      return img_thr + (j >> 1) * (2 * TC_STAGE_FLOATS) + (j & 1) * 256 + (b >> 1) * 512 + (((2 * (b & 1) + (cq >> 1)) ^ (pp & 3)) << 3);
+      return img_thr + (j >> 1) * (2 * TC_STAGE_FLOATS) + (j & 1) * 256 + (b >> 1) * TC_STAGE_FLOATS + (2 * (b & 1)) * 512 +
+             ((img_swz ^ (pp & 3)) << 3);
     };
     int nzs = 0;  // Zbar spills published
     int mj = 0;   // adjoint / forward MMA jobs waited for
@@ -539,13 +557,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     };
     // cross-CTA signalling: every thread fences, one elected lane per warp arrives
     const uint32_t op_ready_leader = mapa_u32(op_ready, 0), rb_free_leader = mapa_u32(rb_free, 0);
+    int nsl = 0;  // slices handed over (selects the barrier)
     // The operand image is read by this SM's own tensor core only, so a CTA-scope proxy fence per thread is enough;
     // the arrive itself is relaxed: a releasing arrive would first wait for this thread's spill stores to reach L2.
-    auto signal_ready = [&]() {   // this thread's part of the operand image is written (and its TMEM reads are done)
+    auto signal_slice = [&]() {   // this warp's part of one 64-feature slice is written (and its TMEM reads are done)
       tc_fence_before();
       fence_async_proxy_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster_relaxed(op_ready_leader);
+      if (lane == 0) mbar_arrive_cluster_relaxed(op_ready_leader + 8u * (uint32_t)(nsl & 3));
+      ++nsl;
+    };
+    const uint32_t edge_ready_leader = mapa_u32(edge_ready, 0);
+    auto signal_edge = [&]() {
+      tc_fence_before();
+      fence_async_proxy_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_relaxed(edge_ready_leader);
     };
     auto publish_spill = [&](uint64_t* bar) {   // this thread's spill stores -> visible to both CTAs' TMA engines at L2
       __threadfence();          // every thread: its own stores are performed at GPU scope ...
@@ -557,9 +584,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       }
     };
     // all four jets of this thread's point for the 4 features of block b: v[j][2u+e]
-    auto ld_block = [&](int b, float (&v)[4][4]) {
+    auto ld_block = [&](int b, float (&v)[4][4], uint32_t buf = 0u) {
       uint32_t ra[8], rb[8];
-      const uint32_t col = (uint32_t)(cbase + 16 * b);
+      const uint32_t col = buf * 256u + (uint32_t)(64 * b + 16 * half);
       tmem_ld_16x256b_x2_nowait(tmem_sp + col, ra);
       tmem_ld_16x256b_x2_nowait(tmem_sp + (16u << 16) + col, rb);
       tmem_wait_ld();
@@ -576,12 +603,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     auto st_op_block = [&](int b, const float (&v)[4][4]) {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        *reinterpret_cast<float4*>(op_thr + 4 * b * OP_LBO + j * 128) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+        *reinterpret_cast<float4*>(op_thr + 16 * b * OP_LBO + j * 128) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
     };
     auto ld_op_block = [&](int b, float (&v)[4][4]) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 t = *reinterpret_cast<const float4*>(op_thr + 4 * b * OP_LBO + j * 128);
+        const float4 t = *reinterpret_cast<const float4*>(op_thr + 16 * b * OP_LBO + j * 128);
         v[j][0] = t.x, v[j][1] = t.y, v[j][2] = t.z, v[j][3] = t.w;
       }
     };
@@ -635,7 +662,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       const float s = b3 ? k0 : k1;
       k += __shfl_xor_sync(0xffffffffu, s, 8);      // holds u = b4, e = b3
       k += __shfl_xor_sync(0xffffffffu, k, 4);
-      if (!(lane & 4)) atomicAdd(dbl + cbase + 16 * b + 4 * cq + 2 * (b4 ? 1 : 0) + (b3 ? 1 : 0), k);
+      if (!(lane & 4)) atomicAdd(dbl + 64 * b + 16 * half + 4 * cq + 2 * (b4 ? 1 : 0) + (b3 ? 1 : 0), k);
     };
 
     for (int it = 0; it < my_tiles; ++it) {
@@ -658,7 +685,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           float z[4][4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int f = cbase + 16 * b + 4 * cq + i;
+            const int f = 64 * b + 16 * half + 4 * cq + i;
             const float4 wa = __ldg(reinterpret_cast<const float4*>(w0p + f * 8));
             const float4 wb = __ldg(reinterpret_cast<const float4*>(w0p + f * 8 + 4));
             const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
@@ -679,19 +706,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           }
           activate(z);
           st_op_block(b, z);
+          signal_slice();
           if (BWD && NHH >= 1) st_img_block(slab + IMG_A, b, z);
         }
       }
       TCT(1)
-      signal_ready();
       // ---------------- hidden layers 1..L-2 on the tensor cores ----------------
       for (int l = 1; l <= L - 2; ++l) {
-        const float* bias_l = A.params + P0 + (long long)(l - 1) * PH + (long long)TC_H * TC_H + cbase + 4 * cq;
+        const float* bias_l = A.params + P0 + (long long)(l - 1) * PH + (long long)TC_H * TC_H + 16 * half + 4 * cq;
         float bl[TC_NBLK][4];
 #pragma unroll
         for (int b = 0; b < TC_NBLK; ++b)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) bl[b][i] = __ldg(bias_l + 16 * b + i);
+          for (int i = 0; i < 4; ++i) bl[b][i] = __ldg(bias_l + 64 * b + i);
         wait_mma();
         TCT(2)
         float* img = slab + (size_t)l * TC_GIMG + IMG_A;
@@ -699,15 +726,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
         for (int b = 0; b < TC_NBLK; ++b) {
           float z[4][4];
-          ld_block(b, z);
+          ld_block(b, z, (uint32_t)(l & 1));   // forward accumulators alternate between the two TMEM halves
 #pragma unroll
           for (int i = 0; i < 4; ++i) z[0][i] += bl[b][i];
           activate(z);
           st_op_block(b, z);
+          signal_slice();   // slice b of a_l is in the operand image: the next job (layer l+1, or 256 -> o) may consume it
           if (spill) st_img_block(img, b, z);
         }
         TCT(1)
-        signal_ready();   // next hidden layer, or (after the last one) the 256 -> o job
       }
       if (BWD) publish_spill(slab_ready);
       TCT(3)
@@ -746,7 +773,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       worker_bar();
       TCT(4)
       if (!BWD) continue;
-      signal_ready();   // the adjoint seeds are in the output image: Abar_{L-2} = seeds * Wlast may start
+      signal_edge();    // the adjoint seeds are in the output image: Abar_{L-2} = seeds * Wlast may start
 
       // =============================== reverse ===============================
       // ---- last layer: dW_last[c][f] = sum_m zbar[m][c] * A[m][f] (thread per feature), db_last ----
@@ -788,11 +815,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           ld_block(b, ab);
           adjoint(ab, act);
           st_op_block(b, ab);
+          signal_slice();                   // (the adjoint job of layer L-2 starts once all four slices are in)
           st_img_block(zdst, b, ab);
           if (L - 3 < TC_MAX_HH) db_block(dbl, b, ab[0]);
         }
       }
-      signal_ready();                       // adjoint job of layer L-2 may start
       publish_spill(&zt_ready[nzs++ & 1]);
       TCT(5)
       // ---- hidden layers L-2 .. 1 ----
@@ -845,16 +872,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             adjoint(ab, act[b]);
             st_op_block(b, ab);
             if (hidden) {
+              signal_slice();               // (the adjoint job of layer l-1 starts once all four slices are in)
               st_img_block(zdst, b, ab);
               if (l - 2 < TC_MAX_HH) db_block(dbl, b, ab[0]);
             }
           }
         }
         TCT(10)
-        if (l > 1) {
-          signal_ready();                   // adjoint job of layer l-1 may start
-          publish_spill(&zt_ready[nzs++ & 1]);
-        }
+        if (l > 1) publish_spill(&zt_ready[nzs++ & 1]);
         TCT(6)
         drain(l);
         TCT(7)
@@ -982,7 +1007,7 @@ __global__ void pack_tc_kernel(const __grid_constant__ pinn_desc_t D, const floa
 // --------------------------------------------------------------------------------------- host side
 constexpr size_t tc_smem_bytes() {
   return (size_t)OP_BYTES + (size_t)TC_STAGES * TC_STAGE_BYTES +
-         (size_t)TC_M * 8 * 4 + (size_t)TC_TP * 8 * 4 + (size_t)TC_MAX_HH * TC_H * 4 + PINN_NSUMS * 8 + (3 * TC_STAGES + 7) * 8 + 16;
+         (size_t)TC_M * 8 * 4 + (size_t)TC_TP * 8 * 4 + (size_t)TC_MAX_HH * TC_H * 4 + PINN_NSUMS * 8 + (3 * TC_STAGES + 11) * 8 + 16;
 }
 
 // Can this description run on the tensor-core kernel?  (otherwise the caller reports UNSUPPORTED)
