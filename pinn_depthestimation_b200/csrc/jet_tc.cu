@@ -261,6 +261,10 @@ struct TileJets {  // output jets of one point, row = 32*(p/8) + 8*j + p%8
 #define TCT(i)
 #endif
 
+#ifdef PINN_TC_DEBUG
+__shared__ long long dbg_t_issue[8];    // producer: when the copy of a stage was issued
+__shared__ long long dbg_t_commit[8];   // issuer: when the commit releasing a stage was issued
+#endif
 template <bool BWD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     jet_tc_kernel(const __grid_constant__ pinn_desc_t D, const __grid_constant__ TcArgs A) {
@@ -347,14 +351,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     if (lane == 0) {
       int ps = 0, nzt = 0;
       uint32_t pph = 1;     // parity to wait for on empty[ps] (first pass: fresh barriers count as released)
+#ifdef PINN_TC_DEBUG
+      long long d_wake = 0, d_nwake = 0;
+#endif
       auto load_n = [&](const float* src, uint32_t bytes) {
         mbar_wait(&empty[ps], pph);
+#ifdef PINN_TC_DEBUG
+        { const long long now = clock64(); if (dbg_t_commit[ps] > 0) { d_wake += now - dbg_t_commit[ps]; ++d_nwake; } dbg_t_issue[ps] = now; }
+#endif
         mbar_expect_tx(&full[ps], bytes);
         tma_load_1d(ring + ps * TC_STAGE_BYTES, src, bytes, &full[ps]);
         if (++ps == TC_STAGES) ps = 0, pph ^= 1u;
       };
       auto load = [&](const float* src) { load_n(src, TC_STAGE_BYTES); };
       const size_t half_off = (size_t)rank * (TC_H * TC_H / 2);
+#ifdef PINN_TC_DEBUG
+      for (int q = 0; q < 8; ++q) dbg_t_commit[q] = 0;
+#endif
       for (int it = 0; it < my_tiles; ++it) {
         for (int hl = 0; hl < NHH; ++hl)
           for (int c = 0; c < TC_WCHUNKS; ++c)
@@ -376,6 +389,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           }
         }
       }
+#ifdef PINN_TC_DEBUG
+      if (blockIdx.x == 0 && d_nwake) printf("TC producer: commit -> producer re-issue %lld cycles avg over %lld stages\n", d_wake / d_nwake, d_nwake);
+#endif
     }
   } else if (warp == TC_WORKERS / 32 + 1) {
     // =========================================== MMA issuer =========================================
@@ -412,7 +428,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       uint32_t rs = 0;      // ring stage of the next chunk
       int jobs = 0, nB = 0;
 #ifdef PINN_TC_DEBUG
-      long long iw_ready = 0, iw_full = 0, iw_peer = 0, iw_rb = 0, i_gemm = 0, i_dw = 0, iw_full_g = 0, iw_peer_g = 0;
+      long long iw_ready = 0, iw_full = 0, iw_peer = 0, iw_rb = 0, i_gemm = 0, i_dw = 0, iw_full_g = 0, iw_peer_g = 0, d_lat = 0, d_nlat = 0, d_lat_dw = 0, d_nlat_dw = 0;
 #define ITM(acc, stmt) { const long long a_ = clock64(); stmt; acc += clock64() - a_; }
 #else
 #define ITM(acc, stmt) stmt;
@@ -438,6 +454,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           if (pipelined && (c & 1) == 0) wait_slice();
           const uint32_t s = rs;
           ITM(iw_full_g, mbar_wait(&full[s], rp))
+#ifdef PINN_TC_DEBUG
+          { d_lat += clock64() - dbg_t_issue[s]; ++d_nlat; }
+#endif
           ITM(iw_peer_g, mbar_wait(&full_peer[s], rp))
           const uint64_t bd = bd_k + (uint64_t)(s * (uint32_t)STG);
 #pragma unroll
@@ -447,6 +466,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
                       idesc_k, kstep > 0 ? 1u : 0u);
           }
           umma_commit(&empty[s]);
+#ifdef PINN_TC_DEBUG
+          dbg_t_commit[s] = clock64();
+#endif
           if (++rs == TC_STAGES) rs = 0, rp ^= 1u;
         }
         umma_commit(mma_done);
@@ -496,6 +518,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             for (int q = 0; q < 16; ++q) {
               const uint32_t s = rs;
               ITM(iw_full, mbar_wait(&full[s], rp))
+#ifdef PINN_TC_DEBUG
+              { d_lat_dw += clock64() - dbg_t_issue[s]; ++d_nlat_dw; }
+#endif
               ITM(iw_peer, mbar_wait(&full_peer[s], rp))
               const uint64_t dd = d_mn + (uint64_t)(s * (uint32_t)STG);
 #pragma unroll
@@ -503,6 +528,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
                 umma_tf32(tmem_base + 256u, dd + (uint64_t)(kk * 64), dd + (uint64_t)(512 + kk * 64), idesc_mn,
                           (q > 0 || kk > 0) ? 1u : 0u);
               umma_commit(&empty[s]);
+#ifdef PINN_TC_DEBUG
+              dbg_t_commit[s] = clock64();
+#endif
               if (++rs == TC_STAGES) rs = 0, rp ^= 1u;
             }
             umma_commit(mma_done_b);
@@ -514,6 +542,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         }
       }
 #ifdef PINN_TC_DEBUG
+      if (blockIdx.x == 0)
+        printf("TC ring: copy issue -> seen full by the issuer: weights %lld cycles avg, weight-gradient operands %lld cycles avg\n",
+               d_lat / (d_nlat ? d_nlat : 1), d_lat_dw / (d_nlat_dw ? d_nlat_dw : 1));
       if (blockIdx.x == 0)
         printf("TC issuer (cycles per tile pair): wait op_ready %lld | fwd+adj jobs %lld (14) | dW jobs %lld (7) | gemm waits: full %lld, peer %lld | dW waits: full %lld, peer %lld, rb_free %lld\n",
                iw_ready / my_tiles, i_gemm / my_tiles, i_dw / my_tiles, iw_full_g / my_tiles, iw_peer_g / my_tiles, iw_full / my_tiles, iw_peer / my_tiles, iw_rb / my_tiles);
