@@ -1046,6 +1046,7 @@ bool tc_supported(const pinn_desc_t* D, const char** why) {
   const int L = D->n_linear;
   *why = "";
   if (L < 3) return *why = "needs at least two hidden layers", false;
+  if (L - 2 > TC_MAX_HH) return *why = "at most 8 hidden layers (bias gradients of 7 hidden->hidden layers are staged in shared memory)", false;
   for (int i = 1; i < L; ++i)
     if (D->widths[i] != TC_H) return *why = "every hidden layer must be 256 wide", false;
   if (D->activation != PINN_ACT_TANH) return *why = "tanh activation only", false;

@@ -101,3 +101,38 @@ def test_tf32_is_refused_for_nets_it_does_not_cover():
                     fields={"U": 0, "V": 1, "h": 2}, target_cols=[0, 1], precision="tf32")
     with pytest.raises(RuntimeError, match="tf32"):
         JetLoss(spec, torch.zeros(8, 2, device=dev), torch.zeros(8, 2, device=dev))
+
+
+def test_tf32_is_refused_for_nets_deeper_than_the_bias_gradient_staging():
+    from pinn_depthestimation_b200 import PassSpec
+    from pinn_depthestimation_b200.fused import JetLoss
+    dev = torch.device("cuda:0")
+    spec = PassSpec(layers=[2] + [256] * 9 + [3], kind="continuity_only", dirs={"x": 0, "y": 1},
+                    fields={"U": 0, "V": 1, "h": 2}, target_cols=[0, 1], precision="tf32")
+    with pytest.raises(RuntimeError, match="tf32|hidden"):
+        JetLoss(spec, torch.zeros(8, 2, device=dev), torch.zeros(8, 2, device=dev))
+
+
+@pytest.mark.parametrize("hidden", [2, 5])
+def test_tf32_other_depths_agree_with_fp32_kernel(hidden):
+    """2 hidden layers = ONE tensor-core job per direction (accumulator parity, slab indexing at the edge); 5 = odd count."""
+    from pinn_depthestimation_b200 import PassSpec
+    from pinn_depthestimation_b200.fused import JetLoss
+    dev = torch.device("cuda:0")
+    layers = [4] + [256] * hidden + [4]
+    kw = dict(dirs={"t": 0, "x": 1, "y": 2}, fields={"h": 0, "z": 1, "u": 2, "v": 3}, target_cols=[0, 1, 2, 3])
+    flat = torch.from_numpy(jo.make_params(layers, 1234, "tanh", np.float32)).to(dev)
+    g = torch.Generator(device="cpu").manual_seed(11)
+    n = 32 * 7 + 5                                   # odd number of tiles: one padding tile in the last pair
+    X = (torch.rand(n, 4, generator=g) * 2 - 1).to(dev)
+    T = (0.05 * torch.randn(n, 4, generator=g)).to(dev)
+    res = {}
+    for prec in ("fp32", "tf32"):
+        jl = JetLoss(PassSpec(layers=layers, kind="Navier_Stokes", precision=prec, **kw), X, T)
+        grad = torch.empty_like(flat)
+        parts = jl.loss_and_grad(flat, grad).clone()
+        torch.cuda.synchronize()
+        res[prec] = (parts, grad)
+    assert torch.isfinite(res["tf32"][1]).all()
+    assert abs(res["tf32"][0][2].item() - res["fp32"][0][2].item()) <= TF32_LOSS_RTOL * abs(res["fp32"][0][2].item())
+    assert ((res["tf32"][1] - res["fp32"][1]).norm() / res["fp32"][1].norm()).item() <= TF32_GRAD_RTOL
