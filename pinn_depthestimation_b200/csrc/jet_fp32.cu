@@ -334,6 +334,52 @@ __global__ void __launch_bounds__(NT)
         //      interleaved rows so that a quarter-warp's LDS.128 hit 32 distinct banks ----
         {
           const int KQ = KP / 4, NQ = NP / 4;
+          if ((KQ & 1) == 0) {
+            // 4 x 8 micro-tiles (two interleaved K groups per thread): 12 LDS.128 per 128 FFMA instead of 8 per 64
+            const int KH = KQ / 2;
+            for (int mt = tid; mt < KH * NQ; mt += NT) {
+              const int gn = mt / KH, g = mt - gn * KH;
+              float w[4][8];
+#pragma unroll
+              for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) w[a][b] = 0.f;
+              const float* zr[4];
+              const float* ar[8];
+#pragma unroll
+              for (int a = 0; a < 4; ++a) zr[a] = bz + (gn + a * NQ) * MP;
+#pragma unroll
+              for (int b = 0; b < 8; ++b) ar[b] = ba + (g + (b >> 2) * KH + (b & 3) * KQ) * MP;
+#pragma unroll 2
+              for (int m = 0; m < M; m += 4) {
+                float4 zv[4], av[8];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) zv[a] = *reinterpret_cast<const float4*>(zr[a] + m);
+#pragma unroll
+                for (int b = 0; b < 8; ++b) av[b] = *reinterpret_cast<const float4*>(ar[b] + m);
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                  for (int b = 0; b < 8; ++b) {
+                    w[a][b] = fmaf(zv[a].x, av[b].x, w[a][b]);
+                    w[a][b] = fmaf(zv[a].y, av[b].y, w[a][b]);
+                    w[a][b] = fmaf(zv[a].z, av[b].z, w[a][b]);
+                    w[a][b] = fmaf(zv[a].w, av[b].w, w[a][b]);
+                  }
+              }
+#pragma unroll
+              for (int a = 0; a < 4; ++a) {
+                const int n = gn + a * NQ;
+                if (n < Nn) {
+#pragma unroll
+                  for (int b = 0; b < 8; ++b) {
+                    const int k = g + (b >> 2) * KH + (b & 3) * KQ;
+                    if (k < K) atomicAdd(A.grad + poff + n * K + k, w[a][b]);
+                  }
+                }
+              }
+            }
+          } else
           for (int mt = tid; mt < KQ * NQ; mt += NT) {
             const int gn = mt / KQ, g = mt - gn * KQ;
             float w[4][4];
