@@ -738,7 +738,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           activate(z);
           st_op_block(b, z);
           signal_slice();
-          if (BWD && NHH >= 1) st_img_block(slab + IMG_A, b, z);
+        }
+        // the spill of a_0 is re-read from the operand image AFTER the last slice has been handed over: its stores stall
+        // on the LSU queue, and the tensor core should already be running layer 1 while they drain
+        if (BWD && NHH >= 1) {
+#pragma unroll
+          for (int b = 0; b < TC_NBLK; ++b) {
+            float z[4][4];
+            ld_op_block(b, z);
+            st_img_block(slab + IMG_A, b, z);
+          }
         }
       }
       TCT(1)
@@ -763,7 +772,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           activate(z);
           st_op_block(b, z);
           signal_slice();   // slice b of a_l is in the operand image: the next job (layer l+1, or 256 -> o) may consume it
-          if (spill) st_img_block(img, b, z);
+        }
+        if (spill) {        // spill from the operand image once all slices are handed over (see layer 0)
+#pragma unroll
+          for (int b = 0; b < TC_NBLK; ++b) {
+            float z[4][4];
+            ld_op_block(b, z);
+            st_img_block(img, b, z);
+          }
         }
         TCT(1)
       }
