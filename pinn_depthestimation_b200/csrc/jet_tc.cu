@@ -5,13 +5,21 @@
 // flat weight gradient.  Here the 256x256 hidden layers -- >99 % of the FLOPs -- run on the 5th-gen
 // tensor cores:
 //
-//   tile            32 points x 4 jet rows = 128 rows                          -> UMMA M = 128
-//   forward  l      D[128 x 256] = A[128 x 256] * W_l^T          A: smem (K-major), B: W image via TMA
-//   adjoint  l      D[128 x 256] = Zbar[128 x 256] * W_l         A: smem (K-major), B: W^T image via TMA
-//   weight grad l   D[256 x 256] = Zbar^T * A_in  (two M=128 halves, K = 128 rows)
-//                                              A, B: MN-major (SWIZZLE_128B_BASE32B) images via TMA
+//   CTA pair        two CTAs (one cluster) work on two tiles in lock step; the leader's MMA warp issues
+//                   tcgen05.mma.cta_group::2 for both (M = 256 = 2 x 128 rows); every B operand is split in
+//                   halves, each CTA streaming only its own
+//   tile            32 points x 4 jet rows = 128 rows per CTA
+//   forward  l      D[256 x 256] = A[256 x 256] * W_l^T          A: smem (K-major), B: W half-images via TMA
+//   adjoint  l      D[256 x 256] = Zbar[256 x 256] * W_l         A: smem (K-major), B: W^T half-images via TMA
+//   weight grad l   D[256 x 256] = Zbar^T * A_in, K = the 256 rows of BOTH tiles; CTA r ends up with dW rows
+//                   [128 r, 128 r + 128)           A, B: MN-major (SWIZZLE_128B_BASE32B) spill pieces via TMA
+//   last layer      forward D[256 x 32] = A * W_last^T (N = 32, zero-padded); reverse Abar = seeds * W_last as
+//                   ONE K = 8 MMA whose A operand is the K-major output / seed image
 //   accumulators live in TMEM (512 columns), read back with tcgen05.ld for the tanh / jet / adjoint
-//   epilogues; the d->256 and 256->o edge layers (<1 % of the work) stay on the FP32 pipes.
+//   epilogues; only the d->256 layer stays on the FP32 pipes.  Forward jobs alternate between TMEM columns
+//   0..255 and 256..511 and consume the operand image in four 64-feature slices, so layer l+1 starts while the
+//   epilogue of layer l is still running; in the reverse sweep columns 256..511 hold the weight-gradient
+//   accumulator.
 //
 // Row order inside a tile: row m = 32*sp + 8*j + pp holds jet j of point 8*sp + pp (sp = TMEM
 // subpartition).  A tcgen05.ld.16x256b hands thread T of a warp the rows pp = T/4 and pp + 8 and two
@@ -19,10 +27,11 @@
 // features: the tanh' coupling between the value and the tangent rows is thread-local (no shuffles) and
 // tanh is evaluated once per (point, feature).
 //
-// Warp roles (576 threads, one CTA per SM, persistent over tiles):
-//   warps 0-15 workers: edge layers, epilogues (TMEM -> registers -> operand image in smem / spill / RED)
-//   warp  16   producer: 1-D TMA bulk copies of weight images and spill chunks into a 4-stage ring
-//   warp  17   MMA issuer: one thread issues tcgen05.mma and tcgen05.commit; owns the TMEM allocation
+// Warp roles (576 threads, one CTA per SM, persistent over tile pairs):
+//   warps 0-15 workers: layer 0, epilogues (TMEM -> registers -> operand image in smem / spill), drains (RED)
+//   warp  16   producer: 1-D TMA bulk copies of weight half-images and spill pieces into a 5-stage ring
+//   warp  17   leader: one thread issues every tcgen05.mma / tcgen05.commit of the pair; follower: one lane per
+//              ring stage relays "my stage has landed" to the leader; owns the TMEM allocation
 //
 // Operand image in shared memory (K-major, no swizzle): element (row m, feature f) at byte
 //   (f/4)*OP_LBO + m*16 + (f%4)*4, OP_LBO = 128*16 + 32: the canonical K-major UMMA layout with
