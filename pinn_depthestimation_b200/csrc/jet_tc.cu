@@ -402,6 +402,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       if (blockIdx.x == 0 && d_nwake) printf("TC producer: commit -> producer re-issue %lld cycles avg over %lld stages\n", d_wake / d_nwake, d_nwake);
 #endif
     }
+#ifdef PINN_TC_DEBUG
+    else if (lane <= TC_STAGES) {
+      // debug pollers: lane s+1 measures, for ring stage s, the time from the copy's issue to its landing
+      const int s = lane - 1;
+      const int per_tile = NHH * TC_WCHUNKS + 1 + (BWD ? 1 + NHH * (TC_WCHUNKS + 16) : 0);
+      const long long total = (long long)my_tiles * per_tile;
+      const long long passes = (total - s + TC_STAGES - 1) / TC_STAGES;
+      long long acc = 0, mx = 0;
+      uint32_t par = 0;
+      for (long long c = 0; c < passes; ++c) {
+        mbar_wait(&full[s], par);
+        const long long dt = clock64() - dbg_t_issue[s];
+        acc += dt;
+        mx = dt > mx ? dt : mx;
+        par ^= 1u;
+      }
+      if (blockIdx.x == 0) printf("TC ring stage %d: copy issue -> landed %lld cycles avg, %lld max (%lld copies)\n", s, acc / (passes ? passes : 1), mx, passes);
+    }
+#endif
   } else if (warp == TC_WORKERS / 32 + 1) {
     // =========================================== MMA issuer =========================================
     if (lane < TC_STAGES && rank != 0) {
