@@ -136,3 +136,55 @@ def test_tf32_other_depths_agree_with_fp32_kernel(hidden):
     assert torch.isfinite(res["tf32"][1]).all()
     assert abs(res["tf32"][0][2].item() - res["fp32"][0][2].item()) <= TF32_LOSS_RTOL * abs(res["fp32"][0][2].item())
     assert ((res["tf32"][1] - res["fp32"][1]).norm() / res["fp32"][1].norm()).item() <= TF32_GRAD_RTOL
+
+
+def test_tf32_properties_at_bench_scale():
+    """Size-independent properties of the tensor-core path at a size no oracle reaches (2^20 points, the bench net):
+    (1) two shards evaluated with the global divisors add up to the single-pass loss and gradient (what the multi-GPU
+        all-reduce relies on; odd cut -> ragged tiles and a padding tile in both shards);
+    (2) the gradient is linear in the loss weights: g(a*fid + b*res) = a*g(fid) + b*g(res)."""
+    from pinn_depthestimation_b200 import PassSpec
+    from pinn_depthestimation_b200.fused import JetLoss
+    layers = [4] + [256] * 8 + [4]
+    n = 1 << 20
+    dev = torch.device("cuda:0")
+    flat = torch.from_numpy(jo.make_params(layers, 1234, "tanh", np.float32)).to(dev)
+    g = torch.Generator(device="cpu").manual_seed(99)
+    X = (torch.rand(n, 4, generator=g) * 2 - 1).to(dev)
+    T = (0.05 * torch.randn(n, 4, generator=g)).to(dev)
+    kw = dict(layers=layers, kind="Navier_Stokes", dirs={"t": 0, "x": 1, "y": 2},
+              fields={"h": 0, "z": 1, "u": 2, "v": 3}, target_cols=[0, 1, 2, 3], precision="tf32")
+
+    def run(spec, x, t, n_global=None):
+        jl = JetLoss(spec, x, t)
+        if n_global is not None:
+            jl.n_res_global = jl.n_fid_global = n_global
+        gr = torch.empty_like(flat)
+        parts = jl.loss_and_grad(flat, gr).clone()
+        torch.cuda.synchronize()
+        return parts, gr, jl.res.sums.clone()
+
+    p_full, g_full, s_full = run(PassSpec(**kw), X, T)
+    assert s_full[13].item() == n and torch.isfinite(g_full).all()
+    # (1) shard additivity
+    cut = 333337
+    acc = torch.zeros_like(flat)
+    sums = torch.zeros(16, dtype=torch.float64, device=dev)
+    for lo, hi in ((0, cut), (cut, n)):
+        _, gi, si = run(PassSpec(**kw), X[lo:hi].contiguous(), T[lo:hi].contiguous(), n_global=n)
+        acc += gi
+        sums += si
+    loss = (sums[0] + sums[1] + sums[2]) / n + sums[5:9].sum() / n
+    assert abs(loss.item() - p_full[2].item()) <= 5e-6 * abs(p_full[2].item())
+    assert ((acc - g_full).norm() / g_full.norm()).item() <= 2e-5
+    assert sums[13].item() == n
+    # (2) linearity in the loss weights
+    _, g_fid, _ = run(PassSpec(w_fid=1.0, w_res=0.0, **kw), X, T)
+    _, g_res, _ = run(PassSpec(w_fid=0.0, w_res=1.0, **kw), X, T)
+    p_mix, g_mix, _ = run(PassSpec(w_fid=0.25, w_res=3.0, **kw), X, T)
+    lin = 0.25 * g_fid + 3.0 * g_res
+    # (the adjoints are rounded to TF32 AFTER the seeds are scaled, so linearity holds to TF32 rounding, not FP32)
+    rel_lin = ((g_mix - lin).norm() / lin.norm()).item()
+    print(f"linearity defect {rel_lin:.2e}")
+    assert rel_lin <= 5e-4
+    assert abs(p_mix[2].item() - (0.25 * p_full[0].item() + 3.0 * p_full[1].item())) <= 5e-6 * abs(p_mix[2].item())
