@@ -47,4 +47,3 @@ for prec in ("fp32", "tf32"):
         nz = np.abs(G) > 0
         print("    nonzero frac", nz.mean(), "rows with nz", nz.any(1).sum(), "cols with nz", nz.any(0).sum())
     if prec == "tf32":
-        print("    debug sums[14] (sum |dW tmem values|):", jl.res.sums.cpu().numpy()[14])
