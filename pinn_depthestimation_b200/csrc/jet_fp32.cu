@@ -313,6 +313,22 @@ __global__ void __launch_bounds__(NT)
     if (BWD) {
       float* bz = cur;  // adjoint of pre-activations of layer l, feature-major
       float* ba = oth;  // input jets of layer l
+      // Wide variant (one 256-thread CTA per SM, registers to spare): the input jets of layer l (= stored output of layer
+      // l-1) are fetched from the slab one iteration ahead, so the global-load latency hides behind the previous layer's
+      // weight-gradient and adjoint loops (+3 %).  The narrow variants load them in place: the 48-64 extra registers
+      // cost them occupancy, which is what their large-N throughput lives on (-9 % measured).
+      constexpr bool PF = NT >= 256;
+      float4 pre[PF ? 4 : 1][PF ? J : 1];
+      auto fetch = [&](int ll) {   // jets that iteration `ll` will copy into `ba`
+        if (PF && ll >= 1 && 4 * cg < pad4(D.widths[ll])) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int j = 0; j < J; ++j)
+              pre[PF ? c : 0][PF ? j : 0] = reinterpret_cast<const float4*>(slab)[(size_t)(((ll - 1) * J + j) * 4 + c) * NT + tid];
+        }
+      };
+      fetch(L - 1);
       for (int l = L - 1; l >= 0; --l) {
         const int K = D.widths[l], Nn = D.widths[l + 1];
         const int KP = pad4(K), NP = pad4(Nn);
@@ -327,8 +343,10 @@ __global__ void __launch_bounds__(NT)
 #pragma unroll
             for (int j = 0; j < J; ++j)
               *reinterpret_cast<float4*>(ba + (4 * cg + c) * MP + j * TP + 4 * pg) =
-                  reinterpret_cast<const float4*>(slab)[(size_t)(((l - 1) * J + j) * 4 + c) * NT + tid];
+                  PF ? pre[PF ? c : 0][PF ? j : 0]
+                     : reinterpret_cast<const float4*>(slab)[(size_t)(((l - 1) * J + j) * 4 + c) * NT + tid];
         }
+        fetch(l - 1);
         __syncthreads();
         // ---- weight gradient: dW[n][k] = sum_m bz[n][m] * ba[k][m]; micro-tiles of 4x4 with
         //      interleaved rows so that a quarter-warp's LDS.128 hit 32 distinct banks ----
