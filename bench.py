@@ -432,8 +432,8 @@ def main():
         peak_src = ("max(cuBLAS TF32 GEMM 8192^3 measured in this run = %.1f TFLOP/s, "
                     "MEASURED_PEAKS.json bf16_tflops_sustained / 2 = %.1f)" % (tf32_meas, bf16 / 2.0))
     # DRAM bytes per point from the committed `ncu --set full` captures of a 1,048,576-point launch
-    # (profiles/r1_fp32_*, r1_tf32_v5_*_ncu_full.csv: dram__bytes_read.sum + dram__bytes_write.sum), scaled to this launch
-    dram_per_point = {"fp32": (0.880954880e9 + 28.288754e9) / 1048576,
+    # (profiles/r1_fp32_v7_*, r1_tf32_v5_*_ncu_full.csv: dram__bytes_read.sum + dram__bytes_write.sum), scaled to this launch
+    dram_per_point = {"fp32": (0.900642048e9 + 28.083769e9) / 1048576,   # profiles/r1_fp32_v7_*
                       "tf32": (23.591678e9 + 61.434800e9) / 1048576}[args.precision]   # profiles/r1_tf32_v5_*
     roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": dram_per_point * (hi - lo),
