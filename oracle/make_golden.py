@@ -63,6 +63,23 @@ CASES = {
     "leaky": dict(layers=[2] + [16] * 4 + [3], activation="leaky_relu", kind=jo.CONT_FTEMP,
                   dirs={"x": 0, "y": 1}, fields={"U": 0, "V": 1, "h": 2},
                   target_cols=[0, 1], n=200, form="single"),
+    # 256-wide nets for the residuals the round-1 tensor-core tests did not cover: physics_equation (divisions by eta+h,
+    # sinh; the last bias keeps the depth h and eta positive like the data, so 1/(eta+h) stays off its pole) and
+    # continuity_ftemp
+    "wide_wave": dict(layers=[2] + [256] * 4 + [6], activation="tanh", kind=jo.WAVE_AVG,
+                      dirs={"x": 0, "y": 1},
+                      fields={"h": 0, "U": 1, "V": 2, "eta_mean": 3, "Hrms": 4, "k": 5},
+                      target_cols=[0, 1, 2, 3, 4, 5], target_w=[1.0, 0.5, 2.0, 1.0, 0.25, 1.5],
+                      last_bias=[2.0, 0.05, -0.03, 0.6, 0.4, 0.9], n=500, form="single"),
+    "wide_ftemp": dict(layers=[2] + [256] * 3 + [3], activation="tanh", kind=jo.CONT_FTEMP,
+                       dirs={"x": 0, "y": 1}, fields={"U": 0, "V": 1, "h": 2},
+                       target_cols=[0, 1], n=500, form="single", w_fid=0.7, w_res=1.3),
+    # physics_equation with the wavenumber output k identically 0: sinh(2kh) = 0, so the (zero-E) radiation-stress terms
+    # are 0 * (0/0) = NaN and the loss is NaN exactly as in the reference (physics.py:106-108)
+    "cmb_nan": dict(layers=[2] + [10] * 3 + [6], activation="tanh", kind=jo.WAVE_AVG,
+                    dirs={"x": 0, "y": 1},
+                    fields={"h": 0, "U": 1, "V": 2, "eta_mean": 3, "Hrms": 4, "k": 5},
+                    target_cols=[0, 1, 2, 3, 4, 5], zero_out_cols=[5], n=64, n_fid=12, form="two_pass"),
     # odd widths (not multiples of 4) and a ragged tile
     "ragged": dict(layers=[3, 7, 13, 5, 4], activation="tanh", kind=jo.NSWE,
                    dirs={"t": 0, "x": 1, "y": 2}, fields={"h": 3, "z": 0, "u": 2, "v": 1},
@@ -99,7 +116,7 @@ def run_reference(case, dtype):
     layers = case["layers"]
     init = "xavier" if case["activation"] == "tanh" else "kaiming"
     model = ref_dnn.DNN(layers, 0.0, init).to(tdt)
-    flat = jo.make_params(layers, 1234, case["activation"], np.float32).astype(dtype)
+    flat = jo.make_case_params(case, dtype)
     _load_flat(model, flat)
     model.train()
     d = layers[0]
@@ -184,8 +201,10 @@ def pack(name, case):
 
 def main():
     torch.set_num_threads(8)
+    only = sys.argv[1:]          # python -m oracle.make_golden [case ...]: regenerate just these
     for name, case in CASES.items():
-        pack(name, case)
+        if not only or name in only:
+            pack(name, case)
 
 
 if __name__ == "__main__":

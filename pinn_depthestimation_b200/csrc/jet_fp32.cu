@@ -578,11 +578,10 @@ static bool is_residual_kind(int k) { return k >= PINN_RES_CONT_ONLY && k <= PIN
 static int uses_tc(const pinn_desc_t* D, bool* tc) {
   *tc = false;
   if (D->precision == PINN_PREC_FP32 || !is_residual_kind(D->residual_kind)) return PINN_OK;
-  if (D->precision == PINN_PREC_TF32X3)
-    return set_error("precision tf32x3 is not available in this build"), PINN_E_UNSUPPORTED;
   const char* why = "";
   if (!tc_supported(D, &why))
-    return set_error("precision tf32 is not available for this net: %s", why), PINN_E_UNSUPPORTED;
+    return set_error("precision %s is not available for this net: %s",
+                     D->precision == PINN_PREC_TF32X3 ? "tf32x3" : "tf32", why), PINN_E_UNSUPPORTED;
   *tc = true;
   return PINN_OK;
 }

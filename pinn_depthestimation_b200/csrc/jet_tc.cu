@@ -45,14 +45,31 @@
 //   threads write it straight from registers in full 32-byte sectors and read a_{l-1} back the same way in the
 //   reverse sweep; one CTA of the pair needs exactly one contiguous 16 KB piece per 16 rows (one TMA copy per ring
 //   stage) -- no transposition pass anywhere.
+//
+// Split-operand mode (X3 = true, PINN_PREC_TF32X3): FP32-grade results on the same tensor pipe.  Every operand x is
+// carried as x = hi + lo with hi = tf32(x), lo = tf32(x - hi) (22 mantissa bits together).  A tile holds 16 points;
+// the hi and lo parts of a jet are SEPARATE ROWS of the same 128-row operand image:
+//   row m = 32*sp + 8*a + pp,   a = 2*jj + h (h = 0 hi, 1 lo),   pp = 4*jh + q,   jet j = 2*jh + jj,   point 4*sp + q
+// so the MMA shape, the descriptors, the ring and the spill layout are unchanged and
+//   forward / adjoint l   D = [A_hi; A_lo] * B_hi  then  += [A_hi; A_lo] * B_lo  (weights streamed as hi and lo images);
+//                         the epilogue adds the hi and the lo row of a jet in FP32 -- the small terms accumulate
+//                         in their own TMEM row -- i.e. (A_hi + A_lo)(B_hi + B_lo), all four products
+//   weight grad l         the two K atoms of a 16-row spill piece are the hi rows (kk = 0) and the lo rows (kk = 1) of the
+//                         same (point, jet) set: Zbar_hi^T A_hi + Zbar_hi^T A_lo + Zbar_lo^T A_hi by pairing the atoms through
+//                         the descriptors -- no second spill image
+// A thread's four row slots (a = 0..3) hold two jets (hi, lo) of ONE point; the partner lane (lane ^ 16) holds the other
+// two, so the tanh' coupling costs a few warp shuffles.  tanhf instead of tanh.approx.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "residual.cuh"
 
 namespace pinn {
 
-constexpr int TC_H = 256;                  // hidden width handled by this kernel
+constexpr int TC_H = 256;                 // hidden width handled by this kernel
 constexpr int TC_M = 128;                  // rows per tile
-constexpr int TC_TP = 32;                  // points per tile
+constexpr int TC_TP = 32;                  // points per tile (TF32 mode; the split-operand mode carries 16, see below)
+constexpr int TC_TP_X3 = 16;
 constexpr int TC_WPS = 4;                  // worker warps per TMEM subpartition
 constexpr int TC_WORKERS = 128 * TC_WPS;
 constexpr int TC_THREADS = TC_WORKERS + 64;
@@ -66,10 +83,10 @@ constexpr int OP_LBO = TC_M * 16 + 32;     // 2080
 constexpr int OP_BYTES = (TC_H / 4) * OP_LBO;
 constexpr int TC_IMG = TC_M * TC_H;        // floats per spill image (one quantity of one layer of one tile)
 constexpr int TC_EDGE_W0 = 0;               // float offsets inside the edge block that follows the hidden-layer weight images
-constexpr int TC_EDGE_WL = TC_H * 8;        //   W0 padded [H][8] | Wlast padded [8][H] | forward-last B images [2][4096] | reverse-last B images [2][1024]
-constexpr int TC_EDGE_E1 = 2 * TC_H * 8;
-constexpr int TC_EDGE_E2 = TC_EDGE_E1 + 2 * TC_STAGE_FLOATS;
-constexpr int TC_EDGE_FLOATS = TC_EDGE_E2 + 2 * 1024;
+constexpr int TC_EDGE_WL = TC_H * 8;        //   W0 padded [H][8] | Wlast padded [8][H] | forward-last B images [rank 2][hi,lo][4096] |
+constexpr int TC_EDGE_E1 = 2 * TC_H * 8;    //   reverse-last B images [rank 2][hi,lo][1024]   (the lo parts are used by the split-operand mode only)
+constexpr int TC_EDGE_E2 = TC_EDGE_E1 + 4 * TC_STAGE_FLOATS;
+constexpr int TC_EDGE_FLOATS = TC_EDGE_E2 + 4 * 1024;
 constexpr int TC_GIMG = 2 * TC_IMG;        // floats per weight-gradient operand image (Zbar_l and a_{l-1} interleaved)
 constexpr int TC_WCHUNKS = TC_H * (TC_H / 2) * 4 / TC_STAGE_BYTES;   // 8 chunks per half-width weight image
 constexpr int TC_MAX_HH = 7;               // hidden->hidden layers whose bias gradients are staged in shared memory
@@ -90,7 +107,29 @@ struct TcArgs {
   int n_tiles;
   float inv_n_res;
   float inv_n_fid;
+  float comp_dw;          // split-operand mode: accumulator-truncation compensation of the weight-gradient jobs (see x3_comp)
 };
+
+// The tensor core updates its FP32 accumulator with round-toward-zero, once per MMA instruction
+// (tools/umma_acc_probe.cu: the TMEM result equals acc <- RZ(acc + exact sum of the 8 products) bit for bit; a K = 256
+// contraction of positive numbers comes out 1.4e-6 low).  Truncation always pulls towards zero, so over the n instructions
+// that accumulate into one TMEM word the expected loss is a fraction of an ulp of every partial sum -- to first order
+// proportional to the partial sums themselves, hence to the result: about kappa * (n + 1) / 2 of it.  At TF32 noise
+// (5e-4) that is invisible; at the 3xTF32 level it is the leading error (every layer shrinks its output by ~1.4e-6, a
+// 256x8 net loses 1.6e-5 of its gradient norm with an angular error of only 2.6e-6).  The split-operand mode therefore
+// scales what it feeds the accumulators by 1 + kappa (n + 1) / 2: folded into the packed weight images for the forward /
+// adjoint jobs (n = 64 instructions per accumulator) and applied in the drain for the weight-gradient jobs (n = 48).
+// kappa = the mean truncation loss per instruction, half an ulp, relative to the value: an ulp is 2^-23 / m of a number
+// with mantissa m in [1,2), and E[1/m] = 1/(2 ln 2) for log-uniform m, so kappa = 2^-24 / (2 ln 2) = 4.30e-8.  The sweep in
+// profiles/r2_x3_calib.log (tools/x3_calib.py, PINN_X3_KAPPA overrides the constant) puts the zero crossing of the scale
+// error at 3.8e-8 .. 4.6e-8 for five nets of depth 2..8: with it the loss error drops from 1.7e-5 to <= 3e-6 and the
+// gradient error from 1.6e-5 to <= 3e-6 (what is left is the angular part).
+constexpr float TC_X3_KAPPA = 4.30e-8f;
+inline float x3_kappa() {
+  const char* e = getenv("PINN_X3_KAPPA");
+  return e ? (float)atof(e) : TC_X3_KAPPA;
+}
+inline float x3_comp(int n_instr) { return 1.0f + x3_kappa() * 0.5f * (float)(n_instr + 1); }
 
 // ------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -253,10 +292,16 @@ __device__ __forceinline__ float4 ld_global_v4(const float* p) {
 // Output jets / adjoint seeds of a tile live in a K-major UMMA operand image [k/4 (2)][row (128)][4] (the A operand of
 // the reverse last-layer MMA): element (row m, output column c) at float (c/4)*512 + m*4 + c%4.
 __device__ __forceinline__ int outs_idx(int m, int c) { return (c >> 2) * 512 + m * 4 + (c & 3); }
-struct TileJets {  // output jets of one point, row = 32*(p/8) + 8*j + p%8
+// row of jet j of point p of a tile (split-operand mode: its hi row; the lo row is 8 further)
+template <bool X3>
+__device__ __forceinline__ int tile_row(int p, int j) {
+  return X3 ? 32 * (p >> 2) + 16 * (j & 1) + 4 * (j >> 1) + (p & 3) : 32 * (p >> 3) + 8 * j + (p & 7);
+}
+template <bool X3>
+struct TileJets {  // output jets of one point
   float* outs;
   int p;
-  __device__ __forceinline__ int row(int j) const { return 32 * (p >> 3) + 8 * j + (p & 7); }
+  __device__ __forceinline__ int row(int j) const { return tile_row<X3>(p, j); }
   __device__ __forceinline__ float get(int col, int j) const { return outs[outs_idx(row(j), col)]; }
   __device__ __forceinline__ void set(int col, int j, float v) { outs[outs_idx(row(j), col)] = v; }
   __device__ __forceinline__ void add(int col, int j, float v) { outs[outs_idx(row(j), col)] += v; }
@@ -274,9 +319,13 @@ struct TileJets {  // output jets of one point, row = 32*(p/8) + 8*j + p%8
 __shared__ long long dbg_t_issue[8];    // producer: when the copy of a stage was issued
 __shared__ long long dbg_t_commit[8];   // issuer: when the commit releasing a stage was issued
 #endif
-template <bool BWD>
+template <bool BWD, bool X3>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     jet_tc_kernel(const __grid_constant__ pinn_desc_t D, const __grid_constant__ TcArgs A) {
+  constexpr int TP = X3 ? TC_TP_X3 : TC_TP;       // points per tile
+  constexpr int XP = X3 ? 2 : 1;                  // weight images per product (hi, lo)
+  constexpr size_t LSTRIDE = (size_t)(2 * XP) * TC_H * TC_H;   // packed floats per hidden layer: [fwd hi][adj hi]([fwd lo][adj lo])
+  constexpr size_t LO_OFF = (size_t)2 * TC_H * TC_H;           // offset of the lo images inside a layer's block
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* op = smem_raw;                                   // operand image (A or Zbar)
   unsigned char* ring = op + OP_BYTES;
@@ -318,7 +367,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   const long long P0 = (long long)d * TC_H + TC_H;               // params of layer 0
   const long long PH = (long long)TC_H * TC_H + TC_H;            // params of a hidden->hidden layer
   const long long poffL = P0 + (long long)NHH * PH;              // params offset of the last layer
-  const float* edge = A.packed + (size_t)NHH * 2 * TC_H * TC_H;  // edge-layer block of the packed weights
+  const float* edge = A.packed + (size_t)NHH * LSTRIDE;          // edge-layer block of the packed weights
   const float* w0p = edge + TC_EDGE_W0;                          // [H][8]  W0[f][c], zero-padded (L1-resident)
 
   // ---------------- one-time setup ----------------
@@ -380,15 +429,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       for (int it = 0; it < my_tiles; ++it) {
         for (int hl = 0; hl < NHH; ++hl)
           for (int c = 0; c < TC_WCHUNKS; ++c)
-            load(A.packed + (size_t)hl * 2 * TC_H * TC_H + half_off + (size_t)c * TC_STAGE_FLOATS);
-        load(edge + TC_EDGE_E1 + (size_t)rank * TC_STAGE_FLOATS);   // last layer, forward: 256 x 16 B image of this CTA
+            for (int x = 0; x < XP; ++x)               // (split-operand mode: the hi chunk, then the lo chunk)
+              load(A.packed + (size_t)hl * LSTRIDE + (size_t)x * LO_OFF + half_off + (size_t)c * TC_STAGE_FLOATS);
+        for (int x = 0; x < XP; ++x)                   // last layer, forward: 256 x 16 B image of this CTA
+          load(edge + TC_EDGE_E1 + (size_t)(2 * rank + x) * TC_STAGE_FLOATS);
         if (BWD) {
-          load_n(edge + TC_EDGE_E2 + (size_t)rank * 1024, 4096);    // last layer, reverse: 8 x 128 B image of this CTA
+          load_n(edge + TC_EDGE_E2 + (size_t)rank * 2048, 4096 * XP);   // last layer, reverse: 8 x 128 B image(s) of this CTA
           mbar_wait(slab_ready, (uint32_t)(it & 1));  // both tiles' activation spills are written and fenced
           for (int l = L - 2; l >= 1; --l) {
             for (int c = 0; c < TC_WCHUNKS; ++c)       // adjoint job of layer l
-              load(A.packed + (size_t)(l - 1) * 2 * TC_H * TC_H + (size_t)TC_H * TC_H + half_off +
-                   (size_t)c * TC_STAGE_FLOATS);
+              for (int x = 0; x < XP; ++x)
+                load(A.packed + (size_t)(l - 1) * LSTRIDE + (size_t)x * LO_OFF + (size_t)TC_H * TC_H + half_off +
+                     (size_t)c * TC_STAGE_FLOATS);
             mbar_wait(&zt_ready[nzt & 1], (uint32_t)((nzt >> 1) & 1));  // Zbar_l of both tiles has been spilled
             ++nzt;
             for (int t = 0; t < 2; ++t) {
@@ -406,7 +458,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     else if (lane <= TC_STAGES) {
       // debug pollers: lane s+1 measures, for ring stage s, the time from the copy's issue to its landing
       const int s = lane - 1;
-      const int per_tile = NHH * TC_WCHUNKS + 1 + (BWD ? 1 + NHH * (TC_WCHUNKS + 16) : 0);
+      const int per_tile = NHH * TC_WCHUNKS * XP + XP + (BWD ? 1 + NHH * (TC_WCHUNKS * XP + 16) : 0);
       const long long total = (long long)my_tiles * per_tile;
       const long long passes = (total - s + TC_STAGES - 1) / TC_STAGES;
       long long acc = 0, mx = 0;
@@ -426,7 +478,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     if (lane < TC_STAGES && rank != 0) {
       // follower: relay "my stage has landed" to the leader's issuer (1-D bulk copies cannot signal a peer barrier);
       // one lane per ring stage so the hand-offs of different stages overlap
-      const int per_tile = NHH * TC_WCHUNKS + 1 + (BWD ? 1 + NHH * (TC_WCHUNKS + 16) : 0);
+      const int per_tile = NHH * TC_WCHUNKS * XP + XP + (BWD ? 1 + NHH * (TC_WCHUNKS * XP + 16) : 0);
       const long long total = (long long)my_tiles * per_tile;
       const long long passes = (total - lane + TC_STAGES - 1) / TC_STAGES;
       const uint32_t fp = mapa_u32(&full_peer[lane], 0);
@@ -480,24 +532,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
         for (int c = 0; c < TC_WCHUNKS; ++c) {
           if (pipelined && (c & 1) == 0) wait_slice();
-          const uint32_t s = rs;
-          ITM(iw_full_g, mbar_wait(&full[s], rp))
-#ifdef PINN_TC_DEBUG
-          { d_lat += clock64() - dbg_t_issue[s]; ++d_nlat; }
-#endif
-          ITM(iw_peer_g, mbar_wait(&full_peer[s], rp))
-          const uint64_t bd = bd_k + (uint64_t)(s * (uint32_t)STG);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const int kstep = c * 4 + kk;  // 8 contraction features per MMA = two 16-byte K chunks
-            umma_tf32(tmem_base + dcol, ad_op + (uint64_t)(kstep * (2 * OP_LBO / 16)), bd + (uint64_t)(kk * (2 * (TC_H / 2) * 16 / 16)),
-                      idesc_k, kstep > 0 ? 1u : 0u);
-          }
-          umma_commit(&empty[s]);
+          for (int x = 0; x < XP; ++x) {   // split-operand mode: the same operand rows against the hi, then the lo weight chunk
+            const uint32_t s = rs;
+            ITM(iw_full_g, mbar_wait(&full[s], rp))
 #ifdef PINN_TC_DEBUG
-          dbg_t_commit[s] = clock64();
+            { d_lat += clock64() - dbg_t_issue[s]; ++d_nlat; }
 #endif
-          if (++rs == TC_STAGES) rs = 0, rp ^= 1u;
+            ITM(iw_peer_g, mbar_wait(&full_peer[s], rp))
+            const uint64_t bd = bd_k + (uint64_t)(s * (uint32_t)STG);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const int kstep = c * 4 + kk;  // 8 contraction features per MMA = two 16-byte K chunks
+              umma_tf32(tmem_base + dcol, ad_op + (uint64_t)(kstep * (2 * OP_LBO / 16)), bd + (uint64_t)(kk * (2 * (TC_H / 2) * 16 / 16)),
+                        idesc_k, (kstep > 0 || x > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty[s]);
+#ifdef PINN_TC_DEBUG
+            dbg_t_commit[s] = clock64();
+#endif
+            if (++rs == TC_STAGES) rs = 0, rp ^= 1u;
+          }
         }
         umma_commit(mma_done);
       };
@@ -508,16 +563,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         {
           // last layer forward: D[256 x 32] = OP * Wlast^T (columns >= o are zero), one ring stage
           wait_ready();
-          const uint32_t s = rs;
-          ITM(iw_full_g, mbar_wait(&full[s], rp))
-          ITM(iw_peer_g, mbar_wait(&full_peer[s], rp))
-          const uint64_t bd = bd_last + (uint64_t)(s * (uint32_t)STG);
 #pragma unroll
-          for (int kstep = 0; kstep < TC_H / 8; ++kstep)
-            umma_tf32(tmem_base, ad_op + (uint64_t)(kstep * (2 * OP_LBO / 16)), bd + (uint64_t)(kstep * (2 * 16 * 16 / 16)), idesc_last,
-                      kstep > 0 ? 1u : 0u);
-          umma_commit(&empty[s]);
-          if (++rs == TC_STAGES) rs = 0, rp ^= 1u;
+          for (int x = 0; x < XP; ++x) {
+            const uint32_t s = rs;
+            ITM(iw_full_g, mbar_wait(&full[s], rp))
+            ITM(iw_peer_g, mbar_wait(&full_peer[s], rp))
+            const uint64_t bd = bd_last + (uint64_t)(s * (uint32_t)STG);
+#pragma unroll
+            for (int kstep = 0; kstep < TC_H / 8; ++kstep)
+              umma_tf32(tmem_base, ad_op + (uint64_t)(kstep * (2 * OP_LBO / 16)), bd + (uint64_t)(kstep * (2 * 16 * 16 / 16)), idesc_last,
+                        (kstep > 0 || x > 0) ? 1u : 0u);
+            umma_commit(&empty[s]);
+            if (++rs == TC_STAGES) rs = 0, rp ^= 1u;
+          }
           umma_commit(mma_done);
         }
         if (BWD) {
@@ -530,6 +588,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             ITM(iw_full_g, mbar_wait(&full[s], rp))
             ITM(iw_peer_g, mbar_wait(&full_peer[s], rp))
             umma_tf32(tmem_base, ad_outs, bd_rl + (uint64_t)(s * (uint32_t)STG), idesc_k, 0u);
+            if (X3) umma_tf32(tmem_base, ad_outs, bd_rl + (uint64_t)(s * (uint32_t)STG + 4096 / 16), idesc_k, 1u);   // lo image of W_last
             umma_commit(&empty[s]);
             if (++rs == TC_STAGES) rs = 0, rp ^= 1u;
             umma_commit(mma_done);
@@ -551,10 +610,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 #endif
               ITM(iw_peer, mbar_wait(&full_peer[s], rp))
               const uint64_t dd = d_mn + (uint64_t)(s * (uint32_t)STG);
+              if (X3) {
+                // the two K atoms of a piece are the hi rows and the lo rows of the same jets: hi.hi + hi.lo + lo.hi
+                umma_tf32(tmem_base + 256u, dd, dd + 512u, idesc_mn, q > 0 ? 1u : 0u);
+                umma_tf32(tmem_base + 256u, dd, dd + (uint64_t)(512 + 64), idesc_mn, 1u);
+                umma_tf32(tmem_base + 256u, dd + 64u, dd + 512u, idesc_mn, 1u);
+              } else {
 #pragma unroll
-              for (int kk = 0; kk < 2; ++kk)
-                umma_tf32(tmem_base + 256u, dd + (uint64_t)(kk * 64), dd + (uint64_t)(512 + kk * 64), idesc_mn,
-                          (q > 0 || kk > 0) ? 1u : 0u);
+                for (int kk = 0; kk < 2; ++kk)
+                  umma_tf32(tmem_base + 256u, dd + (uint64_t)(kk * 64), dd + (uint64_t)(512 + kk * 64), idesc_mn,
+                            (q > 0 || kk > 0) ? 1u : 0u);
+              }
               umma_commit(&empty[s]);
 #ifdef PINN_TC_DEBUG
               dbg_t_commit[s] = clock64();
@@ -583,8 +649,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     const int sp = warp & 3, half = warp >> 2;   // the four warps of a subpartition split every 64-feature slice
     const int cbase = half * TC_WCOLS;           // (drain only: contiguous column range of this warp)
     const int pp = lane >> 2, cq = lane & 3;     // point within the subpartition, column pair within 8 columns
-    const int pt = sp * 8 + pp;                  // this thread's point of the tile
-    const int mrow0 = sp * 32 + pp;              // row of its value jet; jet j sits at row mrow0 + 8 j
+    const int pt = X3 ? sp * 4 + (pp & 3) : sp * 8 + pp;   // this thread's point of the tile
+    const int mrow0 = sp * 32 + pp;              // row of its slot 0; slot a sits at row mrow0 + 8 a (TF32 mode: slot = jet;
+                                                 // split-operand mode: slot 2 jj + h = part h of jet 2 jh + jj, jh = pp / 4)
+    const bool lead = lane < 16;                 // split-operand mode: this lane holds jets 0, 1 (the partner lane ^ 16: jets 2, 3)
     const uint32_t tmem_sp = tmem_base + ((uint32_t)(sp * 32) << 16);
     const float inv_cnt = (kind == PINN_RES_CONT_ONLY && A.mask_count) ? 1.0f / *A.mask_count : 0.f;
     // This thread's features in block b = slice b of the layer (64 features), 16 of which belong to this warp.  The rows
@@ -708,6 +776,62 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         ab[3][i] = round_tf32(ab[3][i] * s);
       }
     };
+    // ---- split-operand mode ----
+    // x -> (hi, lo) with hi = tf32(x), lo = tf32(x - hi): written to the thread's slots 2 jj (hi) and 2 jj + 1 (lo)
+    auto split_store = [&](float (&v)[4][4], int i, float x0, float x1) {
+      const float h0 = round_tf32(x0), h1 = round_tf32(x1);
+      v[0][i] = h0, v[1][i] = round_tf32(x0 - h0);
+      v[2][i] = h1, v[3][i] = round_tf32(x1 - h1);
+    };
+    // v: the thread's four accumulator slots of block b (hi and lo rows of its two jets) -> post-activation jets, split.
+    // bias: the layer's bias for the thread's features (added to the value jet, which the lead lane holds).
+    // Each lane evaluates tanh for two of the four features; the pair exchanges pre-activations, s = 1 - a^2 and a.
+    auto activate_x3 = [&](float (&v)[4][4], const float (&bias)[4]) {
+      float z0[4], z1[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        z0[i] = v[0][i] + v[1][i] + (lead ? bias[i] : 0.f);   // lead: value pre-activation; partner: tangent jet 2
+        z1[i] = v[2][i] + v[3][i];                            // lead: tangent jet 1;         partner: tangent jet 3
+      }
+      const float r2 = __shfl_xor_sync(0xffffffffu, z0[2], 16), r3 = __shfl_xor_sync(0xffffffffu, z0[3], 16);
+      const float ta = tanhf(lead ? z0[0] : r2), tb = tanhf(lead ? z0[1] : r3);   // lead: features 0, 1; partner: 2, 3
+      const float sa = fmaf(-ta, ta, 1.f), sb = fmaf(-tb, tb, 1.f);
+      const float osa = __shfl_xor_sync(0xffffffffu, sa, 16), osb = __shfl_xor_sync(0xffffffffu, sb, 16);
+      const float ota = __shfl_xor_sync(0xffffffffu, ta, 16), otb = __shfl_xor_sync(0xffffffffu, tb, 16);
+      const float s[4] = {lead ? sa : osa, lead ? sb : osb, lead ? osa : sa, lead ? osb : sb};
+      const float a[4] = {ta, tb, ota, otb};   // (meaningful in the lead lane only)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split_store(v, i, lead ? a[i] : s[i] * z0[i], s[i] * z1[i]);
+    };
+    // ab: accumulator slots of the adjoint job (adjoint of the post-activation jets), act: the stored post-activation
+    // jets (hi / lo slots) -> ab = Zbar, split; zb0 = the un-split value-row Zbar (lead lanes; for the bias gradient)
+    auto adjoint_x3 = [&](float (&ab)[4][4], const float (&act)[4][4], float (&zb0)[4]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float g0 = ab[0][i] + ab[1][i], g1 = ab[2][i] + ab[3][i];
+        const float c0 = act[0][i] + act[1][i], c1 = act[2][i] + act[3][i];
+        const float prp = lead ? g1 * c1 : fmaf(g0, c0, g1 * c1);   // this lane's part of sum_{j>=1} abar_j * adot'_j
+        const float ex = __shfl_xor_sync(0xffffffffu, lead ? c0 : prp, 16);   // lead receives the partner's part, the partner a'
+        const float a = lead ? c0 : ex;
+        const float sgm = fmaf(-a, a, 1.f);
+        const float x0 = lead ? fmaf(-2.f * a, prp + ex, g0 * sgm) : g0 * sgm;
+        zb0[i] = x0;
+        split_store(ab, i, x0, g1 * sgm);
+      }
+    };
+    // bias gradient, split-operand mode: the value-row Zbar of the warp's 4 points sits in lanes 4 q + cq (< 16):
+    // transposing butterfly over lane bits 3, 2, then one shared-memory atomic per feature (16 lanes)
+    auto db_block_x3 = [&](float* dbl, int b, const float (&zb)[4]) {
+      const bool b3 = lane & 8, b2 = lane & 4;
+      float k0 = b3 ? zb[2] : zb[0], k1 = b3 ? zb[3] : zb[1];
+      const float s0 = b3 ? zb[0] : zb[2], s1 = b3 ? zb[1] : zb[3];
+      k0 += __shfl_xor_sync(0xffffffffu, s0, 8);
+      k1 += __shfl_xor_sync(0xffffffffu, s1, 8);    // holds features 2 b3 + {0, 1}
+      float k = b2 ? k1 : k0;
+      const float sx = b2 ? k0 : k1;
+      k += __shfl_xor_sync(0xffffffffu, sx, 4);     // holds feature 2 b3 + b2, summed over the 4 points
+      if (lead) atomicAdd(dbl + 64 * b + 16 * half + 4 * cq + 2 * (b3 ? 1 : 0) + (b2 ? 1 : 0), k);
+    };
     // bias gradient of a hidden layer: sum over the tile's points of the value-row Zbar.  The 8 points of a
     // warp sit in lanes 4 pp + cq: halving butterfly over lane bits 4, 3, 2, then one shared-memory atomic
     // per feature (16 lanes), accumulated over all tiles and flushed once at kernel exit.
@@ -726,8 +850,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 
     for (int it = 0; it < my_tiles; ++it) {
       const long long tile = 2ll * (pair + (long long)it * n_pairs) + rank;   // may lie past the end: an all-padding tile
-      const long long p0 = tile * TC_TP;
-      for (int i = tid; i < TC_TP * 8; i += TC_WORKERS) {
+      const long long p0 = tile * TP;
+      for (int i = tid; i < TP * 8; i += TC_WORKERS) {
         const int pq = i >> 3, c = i & 7;
         const long long gp = p0 + pq;
         xin[i] = (c < d && gp < A.n_points) ? A.inputs[gp * d + c] : 0.f;
@@ -763,8 +887,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
               z[1 + jj][i] = t;
             }
           }
-          activate(z);
-          st_op_block(b, z);
+          if (X3) {
+            // both lanes of a pair evaluate the (cheap) layer-0 activation; each keeps its two jets, split into hi / lo
+            float v[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float a = tanhf(z[0][i]);
+              const float sg = fmaf(-a, a, 1.f);
+              split_store(v, i, lead ? a : sg * z[2][i], lead ? sg * z[1][i] : sg * z[3][i]);
+            }
+            st_op_block(b, v);
+          } else {
+            activate(z);
+            st_op_block(b, z);
+          }
           signal_slice();
         }
         // the spill of a_0 is re-read from the operand image AFTER the last slice has been handed over: its stores stall
@@ -795,9 +931,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         for (int b = 0; b < TC_NBLK; ++b) {
           float z[4][4];
           ld_block(b, z, (uint32_t)(l & 1));   // forward accumulators alternate between the two TMEM halves
+          if (X3) {
+            activate_x3(z, bl[b]);
+          } else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) z[0][i] += bl[b][i];
-          activate(z);
+            for (int i = 0; i < 4; ++i) z[0][i] += bl[b][i];
+            activate(z);
+          }
           st_op_block(b, z);
           signal_slice();   // slice b of a_l is in the operand image: the next job (layer l+1, or 256 -> o) may consume it
         }
@@ -819,7 +959,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         const int mm = sp * 32 + lane;   // this thread's TMEM lane = tile row
         float v[8];
         tmem_ld_32x32b_x8(tmem_sp, v);
-        if (((mm >> 3) & 3) == 0) {      // value rows carry the bias
+        if (X3) {                        // hi row + lo row of a jet (8 rows apart); both rows keep the sum
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[c] += __shfl_xor_sync(0xffffffffu, v[c], 8);
+        }
+        if (X3 ? ((lane >> 3) == 0 && (lane & 4) == 0) : (((mm >> 3) & 3) == 0)) {      // value rows carry the bias
 #pragma unroll
           for (int c = 0; c < 8; ++c)
             if (c < o) v[c] += __ldg(A.params + poffL + (long long)TC_H * o + c);
@@ -832,10 +976,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       TCT(13)
       // ---------------- residual / misfit epilogue: warp 0, one lane per point ----------------
       if (warp == 0) {
-        const long long gp = p0 + lane;
-        TileJets acc{outs, lane};
+        const bool isp = lane < TP;
+        const int pl = isp ? lane : 0;
+        const long long gp = p0 + pl;
+        TileJets<X3> acc{outs, pl};
         float ls[PINN_NSUMS];
-        residual_epilogue<4>(D, acc, true, gp < A.n_points, gp, xin + lane * 8,
+        residual_epilogue<4>(D, acc, isp, isp && gp < A.n_points, gp, xin + pl * 8,
                              EpiArgs{A.targets, nullptr, {nullptr, nullptr, nullptr}, A.out,
                                      {A.dout[0], A.dout[1], A.dout[2]}, A.inv_n_res, A.inv_n_fid, inv_cnt},
                              ls);
@@ -843,6 +989,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         for (int i = 0; i < PINN_NSUMS; ++i) {
           const float v = warp_sum_tc(ls[i]);
           if (lane == 0 && v != 0.f) red[i] += (double)v;
+        }
+        if (X3 && BWD && isp) {   // adjoint seeds -> hi in the jet's hi row, lo in its lo row (A operand of the reverse last-layer MMA)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int r = acc.row(j);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float x = outs[outs_idx(r, c)];
+              const float hi = round_tf32(x);
+              outs[outs_idx(r, c)] = hi;
+              outs[outs_idx(r + 8, c)] = round_tf32(x - hi);
+            }
+          }
         }
       }
       worker_bar();
@@ -859,9 +1018,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         for (int c = 0; c < 8; ++c) acc[c] = 0.f;
         const unsigned char* ap = op + (f >> 2) * OP_LBO + (f & 3) * 4;
         for (int mm = part * (TC_M / TC_PARTS); mm < (part + 1) * (TC_M / TC_PARTS); ++mm) {
-          const float a = *reinterpret_cast<const float*>(ap + mm * 16);
-          const float4 z0 = *reinterpret_cast<const float4*>(outs + mm * 4);
-          const float4 z1 = *reinterpret_cast<const float4*>(outs + 512 + mm * 4);
+          if (X3 && (mm & 8)) continue;   // split-operand mode: visit the hi rows, add the lo row 8 further
+          float a = *reinterpret_cast<const float*>(ap + mm * 16);
+          float4 z0 = *reinterpret_cast<const float4*>(outs + mm * 4);
+          float4 z1 = *reinterpret_cast<const float4*>(outs + 512 + mm * 4);
+          if (X3) {
+            a += *reinterpret_cast<const float*>(ap + (mm + 8) * 16);
+            const float4 y0 = *reinterpret_cast<const float4*>(outs + (mm + 8) * 4);
+            const float4 y1 = *reinterpret_cast<const float4*>(outs + 512 + (mm + 8) * 4);
+            z0.x += y0.x, z0.y += y0.y, z0.z += y0.z, z0.w += y0.w;
+            z1.x += y1.x, z1.y += y1.y, z1.z += y1.z, z1.w += y1.w;
+          }
           acc[0] = fmaf(z0.x, a, acc[0]), acc[1] = fmaf(z0.y, a, acc[1]);
           acc[2] = fmaf(z0.z, a, acc[2]), acc[3] = fmaf(z0.w, a, acc[3]);
           acc[4] = fmaf(z1.x, a, acc[4]), acc[5] = fmaf(z1.y, a, acc[5]);
@@ -872,7 +1039,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           if (c < o) atomicAdd(A.grad + poffL + (long long)c * TC_H + f, acc[c]);
         if (tid < o) {
           float s = 0.f;
-          for (int pq = 0; pq < TC_TP; ++pq) s += outs[outs_idx(32 * (pq >> 3) + (pq & 7), tid)];
+          for (int pq = 0; pq < TP; ++pq) {
+            const int r = tile_row<X3>(pq, 0);
+            s += outs[outs_idx(r, tid)];
+            if (X3) s += outs[outs_idx(r + 8, tid)];
+          }
           atomicAdd(A.grad + poffL + (long long)TC_H * o + tid, s);
         }
       }
@@ -888,11 +1059,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           float ab[4][4], act[4][4];
           ld_op_block(b, act);
           ld_block(b, ab);
-          adjoint(ab, act);
+          float zb0[4];
+          if (X3) adjoint_x3(ab, act, zb0);
+          else adjoint(ab, act);
           st_op_block(b, ab);
           signal_slice();                   // (the adjoint job of layer L-2 starts once all four slices are in)
           st_img_block(zdst, b, ab);
-          if (L - 3 < TC_MAX_HH) db_block(dbl, b, ab[0]);
+          if (L - 3 < TC_MAX_HH) {
+            if (X3) db_block_x3(dbl, b, zb0);
+            else db_block(dbl, b, ab[0]);
+          }
         }
       }
       publish_spill(&zt_ready[nzs++ & 1]);
@@ -917,6 +1093,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           for (int cb = 0; cb < TC_WCOLS / 32; ++cb) {
             float v[16];
             tmem_ld_16x256b_x4(ta + (uint32_t)(cb * 32), v);
+#pragma unroll
+            if (X3) {
+#pragma unroll
+              for (int u = 0; u < 16; ++u) v[u] *= A.comp_dw;
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               red_add_v2(grow + cb * 32 + 8 * u, v[4 * u], v[4 * u + 1]);
@@ -944,12 +1125,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           for (int b = 0; b < TC_NBLK; ++b) {
             float ab[4][4];
             ld_block(b, ab);
-            adjoint(ab, act[b]);
+            float zb0[4];
+            if (X3) adjoint_x3(ab, act[b], zb0);
+            else adjoint(ab, act[b]);
             st_op_block(b, ab);
             if (hidden) {
               signal_slice();               // (the adjoint job of layer l-1 starts once all four slices are in)
               st_img_block(zdst, b, ab);
-              if (l - 2 < TC_MAX_HH) db_block(dbl, b, ab[0]);
+              if (l - 2 < TC_MAX_HH) {
+                if (X3) db_block_x3(dbl, b, zb0);
+                else db_block(dbl, b, ab[0]);
+              }
             }
           }
         }
@@ -969,14 +1155,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         float acc[8], tj[3] = {0.f, 0.f, 0.f}, sb = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-        for (int pq = part * (TC_TP / TC_PARTS); pq < (part + 1) * (TC_TP / TC_PARTS); ++pq) {
-          const int r0 = 32 * (pq >> 3) + (pq & 7);
-          const float z0 = *reinterpret_cast<const float*>(zp + r0 * 16);
+        for (int pq = part * (TP / TC_PARTS); pq < (part + 1) * (TP / TC_PARTS); ++pq) {
+          auto zrow = [&](int j) {   // Zbar_0 of jet j of point pq for feature f (split-operand mode: hi + lo row)
+            const int r = tile_row<X3>(pq, j);
+            float v = *reinterpret_cast<const float*>(zp + r * 16);
+            if (X3) v += *reinterpret_cast<const float*>(zp + (r + 8) * 16);
+            return v;
+          };
+          const float z0 = zrow(0);
           sb += z0;
 #pragma unroll
           for (int c = 0; c < 8; ++c) acc[c] = fmaf(z0, xin[pq * 8 + c], acc[c]);
 #pragma unroll
-          for (int jj = 0; jj < 3; ++jj) tj[jj] += *reinterpret_cast<const float*>(zp + (r0 + 8 * (1 + jj)) * 16);
+          for (int jj = 0; jj < 3; ++jj) tj[jj] += zrow(1 + jj);
         }
         for (int jj = 0; jj < D.n_dirs; ++jj) {
 #pragma unroll
@@ -1024,12 +1215,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 // in 16 KB chunks of 32 contraction features laid out [k/4 (8)][n (128)][k%4] (K-major, no swizzle):
 //   forward:  B[n][k] = W[n][k]     half = n / 128   (rows n = output feature, contraction k = input feature)
 //   adjoint:  B[n][k] = W[k][n]     half = n / 128   (rows n = input feature,  contraction k = output feature)
+// Split-operand mode (x3): w = hi + lo, hi = tf32(w), lo = tf32(w - hi); a layer's block is [fwd hi][adj hi][fwd lo][adj lo].
 __global__ void pack_tc_kernel(const __grid_constant__ pinn_desc_t D, const float* __restrict__ params,
-                               float* __restrict__ packed) {
+                               float* __restrict__ packed, int x3, float comp) {
   const int hl = blockIdx.y;
   const int d = D.widths[0];
   const long long poff = (long long)d * TC_H + TC_H + (long long)hl * ((long long)TC_H * TC_H + TC_H);
-  float* fwd = packed + (size_t)hl * 2 * TC_H * TC_H;
+  const size_t lstride = (size_t)(x3 ? 4 : 2) * TC_H * TC_H;
+  float* fwd = packed + (size_t)hl * lstride;
   float* adj = fwd + (size_t)TC_H * TC_H;
   auto at = [](int n, int k) {   // float offset of B[n][k] inside its direction's two half-images
     // feature n = 16 g + 4 cq + 2 u + e sits in MMA row 16 g + 8 u + 2 cq + e (see the worker addressing)
@@ -1040,19 +1233,26 @@ __global__ void pack_tc_kernel(const __grid_constant__ pinn_desc_t D, const floa
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < TC_H * TC_H; i += gridDim.x * blockDim.x) {
     const int n = i / TC_H, k = i - n * TC_H;
     uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(params[poff + i]));
+    const float wv = x3 ? params[poff + i] * comp : params[poff + i];   // (comp: see x3_comp)
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(wv));
     const float w = __uint_as_float(r);
     fwd[at(n, k)] = w;
     adj[at(k, n)] = w;
+    if (x3) {
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(wv - w));
+      const float wl = __uint_as_float(r);
+      fwd[2 * TC_H * TC_H + at(n, k)] = wl;
+      adj[2 * TC_H * TC_H + at(k, n)] = wl;
+    }
   }
   if (hl == 0) {   // zero-padded copies of the two edge layers (read with __ldg by every CTA)
     const int L = D.n_linear, o = D.widths[L];
     const long long poffL = (long long)d * TC_H + TC_H + (long long)(L - 2) * ((long long)TC_H * TC_H + TC_H);
-    float* edge = packed + (size_t)(L - 2) * 2 * TC_H * TC_H;
+    float* edge = packed + (size_t)(L - 2) * lstride;
     float* w0p = edge + TC_EDGE_W0;
     float* wlp = edge + TC_EDGE_WL;
-    float* e1 = edge + TC_EDGE_E1;   // forward last layer:  rank 0 [k/4 (64)][n (16)][4] = Wlast[n][k], rank 1 zeros
-    float* e2 = edge + TC_EDGE_E2;   // reverse last layer:  rank r [k/4 (2)][n (128)][4] = Wlast[k][128 r + n], rows permuted
+    float* e1 = edge + TC_EDGE_E1;   // forward last layer:  [rank][hi,lo][k/4 (64)][n (16)][4] = Wlast[n][k] for rank 0, zeros for rank 1
+    float* e2 = edge + TC_EDGE_E2;   // reverse last layer:  [rank][hi,lo][k/4 (2)][n (128)][4] = Wlast[k][128 r + n], rows permuted
     auto tf32 = [](float x) {
       uint32_t r;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -1066,14 +1266,23 @@ __global__ void pack_tc_kernel(const __grid_constant__ pinn_desc_t D, const floa
         wlp[i] = c2 < o ? params[poffL + (long long)c2 * TC_H + f2] : 0.f;
         // reverse image: i = c2 (k, 0..7) * 256 + f2 (feature)
         const int n = f2 & 127, nr = (n & ~15) | (((n >> 1) & 1) << 3) | (((n >> 2) & 3) << 1) | (n & 1);
-        e2[(f2 >> 7) * 1024 + (c2 >> 2) * 512 + nr * 4 + (c2 & 3)] = c2 < o ? tf32(params[poffL + (long long)c2 * TC_H + f2]) : 0.f;
+        const float wv = c2 < o ? params[poffL + (long long)c2 * TC_H + f2] : 0.f;
+        const float wh = tf32(wv);
+        const size_t at2 = (size_t)(f2 >> 7) * 2048 + (c2 >> 2) * 512 + nr * 4 + (c2 & 3);
+        e2[at2] = wh;
+        e2[at2 + 1024] = tf32(wv - wh);
       }
       // forward image: i < 4096: rank 0, i = k * 16 + n; the rest: rank 1 = zeros
       if (i < TC_STAGE_FLOATS) {
         const int k = i >> 4, n = i & 15;
-        e1[(k >> 2) * 64 + n * 4 + (k & 3)] = n < o ? tf32(params[poffL + (long long)n * TC_H + k]) : 0.f;
+        const float wv = n < o ? params[poffL + (long long)n * TC_H + k] * (x3 ? comp : 1.f) : 0.f;
+        const float wh = tf32(wv);
+        const size_t at1 = (size_t)(k >> 2) * 64 + n * 4 + (k & 3);
+        e1[at1] = wh;
+        e1[TC_STAGE_FLOATS + at1] = tf32(wv - wh);
       } else {
-        e1[i] = 0.f;
+        e1[TC_STAGE_FLOATS + i] = 0.f;                      // rank 1, hi
+        e1[2 * TC_STAGE_FLOATS + i] = 0.f;                  // rank 1, lo
       }
     }
   }
@@ -1103,13 +1312,15 @@ bool tc_supported(const pinn_desc_t* D, const char** why) {
 int tc_workspace(const pinn_desc_t* D, long long n_points, int sms, size_t* packed_bytes, size_t* slab_bytes,
                  long long* slab_stride, int* grid) {
   const int L = D->n_linear;
-  long long tiles = (n_points + TC_TP - 1) / TC_TP;
+  const bool x3 = D->precision == PINN_PREC_TF32X3;
+  const int tp = x3 ? TC_TP_X3 : TC_TP;
+  long long tiles = (n_points + tp - 1) / tp;
   long long pairs = (tiles + 1) / 2;
   if (pairs > sms / 2) pairs = sms / 2;
   if (pairs < 1) pairs = 1;
   long long g = 2 * pairs;   // CTA pairs (clusters of 2)
   *grid = (int)g;
-  *packed_bytes = (size_t)(L - 2) * 2 * TC_H * TC_H * 4 + (size_t)TC_EDGE_FLOATS * 4;   // + edge-layer block
+  *packed_bytes = (size_t)(L - 2) * (x3 ? 4 : 2) * TC_H * TC_H * 4 + (size_t)TC_EDGE_FLOATS * 4;   // + edge-layer block
   *slab_stride = (long long)(L - 2) * TC_GIMG;   // one weight-gradient operand image per hidden layer
   *slab_bytes = (size_t)g * (size_t)(*slab_stride) * 4;
   return PINN_OK;
@@ -1129,12 +1340,14 @@ int run_tc_pass(const pinn_desc_t* D, const pinn_eval_args_t* a, bool bwd, void*
   if (bwd && ((uintptr_t)a->grad & 15) != 0) return set_error("grad must be 16-byte aligned for the tensor-core path"), PINN_E_ARG;
   float* packed = reinterpret_cast<float*>(workspace);
   float* slab = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pk_al);
+  const bool x3 = D->precision == PINN_PREC_TF32X3;
   if (!(a->flags & PINN_FLAG_SKIP_PACK)) {
     dim3 g(64, D->n_linear - 2);
-    pack_tc_kernel<<<g, 256, 0, st>>>(*D, a->params, packed);
+    pack_tc_kernel<<<g, 256, 0, st>>>(*D, a->params, packed, x3 ? 1 : 0, x3 ? x3_comp(64) : 1.f);
     PINN_CUDA(cudaGetLastError());
   }
-  long long tiles = (a->n_points + TC_TP - 1) / TC_TP;
+  const int tp = x3 ? TC_TP_X3 : TC_TP;
+  long long tiles = (a->n_points + tp - 1) / tp;
   if (tiles == 0) return PINN_OK;
   if (tiles > 0x7fffffffLL) return set_error("too many tiles"), PINN_E_UNSUPPORTED;
   TcArgs A;
@@ -1153,16 +1366,16 @@ int run_tc_pass(const pinn_desc_t* D, const pinn_eval_args_t* a, bool bwd, void*
   A.n_tiles = (int)tiles;
   A.inv_n_res = a->n_res_global > 0 ? (float)(1.0 / (double)a->n_res_global) : 0.f;
   A.inv_n_fid = a->n_fid_global > 0 ? (float)(1.0 / (double)a->n_fid_global) : 0.f;
+  A.comp_dw = x3 ? x3_comp(48) : 1.f;
   const size_t smem = tc_smem_bytes();
-  if (bwd) {
-    PINN_CUDA(cudaFuncSetAttribute(jet_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    jet_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(*D, A);
-  } else {
-    PINN_CUDA(cudaFuncSetAttribute(jet_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    jet_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(*D, A);
-  }
-  PINN_CUDA(cudaGetLastError());
-  return PINN_OK;
+  auto go = [&](auto kern) -> int {
+    PINN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, TC_THREADS, smem, st>>>(*D, A);
+    PINN_CUDA(cudaGetLastError());
+    return PINN_OK;
+  };
+  if (x3) return bwd ? go(jet_tc_kernel<true, true>) : go(jet_tc_kernel<false, true>);
+  return bwd ? go(jet_tc_kernel<true, false>) : go(jet_tc_kernel<false, false>);
 }
 
 }  // namespace pinn

@@ -30,15 +30,17 @@ __device__ __forceinline__ float block_sum(float v, float* warp_buf) {
   for (int i = 0; i < nw; ++i) t += warp_buf[i];  // fixed order
   return t;
 }
+// max that propagates NaN like torch's abs().max() (fmaxf drops it: a NaN gradient must not look converged)
+__device__ __forceinline__ float nan_max(float a, float b) { return (a != a || b != b) ? __int_as_float(0x7fc00000) : fmaxf(a, b); }
 __device__ __forceinline__ float block_max(float v, float* warp_buf) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  for (int o = 16; o > 0; o >>= 1) v = nan_max(v, __shfl_xor_sync(0xffffffffu, v, o));
   const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   __syncthreads();
   if ((threadIdx.x & 31) == 0) warp_buf[w] = v;
   __syncthreads();
   float t = 0.f;
-  for (int i = 0; i < nw; ++i) t = fmaxf(t, warp_buf[i]);
+  for (int i = 0; i < nw; ++i) t = nan_max(t, warp_buf[i]);
   return t;
 }
 
@@ -157,8 +159,8 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kVecThrea
     const float x = a[i], y = b ? b[i] : 0.f;
     ab = fmaf(x, y, ab);
     l1 += fabsf(x);
-    ma = fmaxf(ma, fabsf(x));
-    mb = fmaxf(mb, fabsf(y));
+    ma = nan_max(ma, fabsf(x));
+    mb = nan_max(mb, fabsf(y));
     aa = fmaf(x, x, aa);
     bb = fmaf(y, y, bb);
   }
@@ -177,7 +179,7 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kVecThrea
     float t = 0.f;
     for (unsigned r = 0; r < cl.num_blocks(); ++r) {
       const float v = *cl.map_shared_rank(part + k, r);
-      t = (k == 2 || k == 3) ? fmaxf(t, v) : t + v;
+      t = (k == 2 || k == 3) ? nan_max(t, v) : t + v;
     }
     out[k] = t;
   }

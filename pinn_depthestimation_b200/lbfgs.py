@@ -345,7 +345,7 @@ class LBFGS(torch.optim.Optimizer):
 
                 loss, g_best, t, ls_func_evals = strong_wolfe(
                     evaluate, lambda h: h.clone(), t, loss, g, gtd, d_norm,
-                    tolerance_change=tolerance_change, max_ls=max_eval - current_evals)
+                    max_ls=max_eval - current_evals)   # torch passes only max_ls: zoom keeps its 1e-9 default
                 if g_best.data_ptr() != g.data_ptr():
                     g.copy_(g_best)
                 vec.axpy_into(flat, b["x0"], t, d)

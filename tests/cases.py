@@ -8,7 +8,8 @@ import numpy as np
 from oracle import jet_oracle as jo
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-ALL = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+NAN = ["cmb_nan"]            # the reference's loss is NaN by construction (physics.py:106-108 with k == 0)
+ALL = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f[:-4] not in NAN)
 SMALL = [n for n in ALL if not n.startswith("wide")]
 
 
@@ -35,7 +36,7 @@ def specs(case):
 def data(case, dtype=np.float32):
     d = case["layers"][0]
     nt = len(case["target_cols"])
-    flat = jo.make_params(case["layers"], 1234, case["activation"], np.float32).astype(dtype)
+    flat = jo.make_case_params(case, dtype)
     if case["form"] == "single":
         X, T = jo.make_points(case["n"], d, nt, seed=1234)
         return flat, X, T, None, None

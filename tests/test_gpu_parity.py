@@ -156,3 +156,16 @@ def test_sums_are_additive_over_shards_at_scale():
     rel = (acc - g_full).norm() / g_full.norm()
     assert rel.item() <= 1e-5
     assert sums[13].item() == n
+
+
+@pytest.mark.parametrize("name", cases.NAN)
+def test_physics_equation_nan_poison_like_the_reference(name):
+    """k == 0 => sinh(2kh) = 0 => the zero-E radiation-stress terms are 0 * (0/0): the reference's loss (and its
+    gradient) are NaN (physics.py:106-108; golden from the real reference).  The fused epilogue must not hide that."""
+    from tests.gpu_util import run_case
+    case, z = cases.load(name)
+    assert np.isnan(z["loss64"])
+    parts, grad, _, _ = run_case(case)
+    assert np.isnan(parts[2]) and np.isnan(parts[1])
+    assert abs(parts[0] - z["fidelity64"]) <= LOSS_RTOL * abs(z["fidelity64"])   # the data misfit is unaffected
+    assert np.isnan(grad).any()

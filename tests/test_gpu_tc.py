@@ -16,7 +16,7 @@ TF32_LOSS_RTOL = 3e-3
 TF32_GRAD_RTOL = 5e-3
 
 
-@pytest.mark.parametrize("name", ["wide_nswe", "wide_cont"])
+@pytest.mark.parametrize("name", ["wide_nswe", "wide_cont", "wide_wave", "wide_ftemp"])
 def test_tf32_matches_reference_golden_within_stated_bound(name):
     from tests.gpu_util import run_case
     case, z = cases.load(name)

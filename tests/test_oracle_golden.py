@@ -82,3 +82,21 @@ def test_empty_mask_gives_nan_loss_like_reference():
                          torch.from_numpy(T.astype(np.float64)))
     assert torch.isnan(q["loss"]) and torch.isfinite(q["grad"]).all()
     np.testing.assert_allclose(r["grad"], q["grad"].numpy(), rtol=0, atol=1e-12 * np.abs(r["grad"]).max())
+
+
+@pytest.mark.parametrize("name", cases.NAN)
+def test_oracles_reproduce_the_reference_nan(name):
+    """physics_equation with k == 0: sinh(2kh) = 0, the zero-E stress terms are 0 * (0/0) and the reference's loss
+    is NaN (physics.py:106-108; golden made by running the real reference).  Both oracles must say NaN too."""
+    case, z = cases.load(name)
+    assert np.isnan(z["loss64"]) and np.isnan(z["loss32"]) and np.isnan(z["residual64"])
+    assert np.isfinite(z["fidelity64"])
+    sres, sfid = cases.specs(case)
+    flat, X, T, Xf, Tf = cases.data(case, np.float64)
+    with np.errstate(all="ignore"):
+        r = jo.two_pass_loss_and_grad(sfid, sres, flat, Xf, Tf, X)
+    assert np.isnan(r["loss"]) and np.isnan(r["residual"])
+    assert abs(r["fidelity"] - z["fidelity64"]) <= 1e-12 * abs(z["fidelity64"])
+    tf = torch.from_numpy
+    b = ap.loss_and_grad(sres, tf(flat), tf(X.astype(np.float64)), None)
+    assert torch.isnan(b["residual"])

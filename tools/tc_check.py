@@ -17,7 +17,7 @@ X, T = X[:n], T[:n]
 ospec, _ = cases.specs(case)
 ref = jo.loss_and_grad(ospec, flat.astype(np.float64), X.astype(np.float64), T.astype(np.float64))
 offs, total = jo.layer_offsets(case["layers"])
-for prec in ("fp32", "tf32"):
+for prec in (sys.argv[3].split(",") if len(sys.argv) > 3 else ("fp32", "tf32")):
     spec, _ = pass_specs(case, prec)
     jl = JetLoss(spec, torch.from_numpy(X).to(dev), torch.from_numpy(T).to(dev))
     p = torch.from_numpy(flat).to(dev)
@@ -34,7 +34,7 @@ for prec in ("fp32", "tf32"):
         ew = np.linalg.norm(gg[ow:ob] - ref["grad"][ow:ob]) / max(np.linalg.norm(ref["grad"][ow:ob]), 1e-30)
         eb = np.linalg.norm(gg[ob:ob + nb] - ref["grad"][ob:ob + nb]) / max(np.linalg.norm(ref["grad"][ob:ob + nb]), 1e-30)
         print(f"    layer {l}: dW rel {ew:.3e}   db rel {eb:.3e}")
-    if prec == "tf32":
+    if prec != "fp32":
         l = len(offs) // 2
         ow, ob = offs[l]
         Hh = case["layers"][l]
@@ -46,4 +46,3 @@ for prec in ("fp32", "tf32"):
         print("    G[:8,0]", G[:8, 0]); print("    R[:8,0]", R[:8, 0])
         nz = np.abs(G) > 0
         print("    nonzero frac", nz.mean(), "rows with nz", nz.any(1).sum(), "cols with nz", nz.any(0).sum())
-    if prec == "tf32":
