@@ -65,7 +65,7 @@ MODE_INFO = {
                               "mode": "3xTF32 split operands (hi+lo), fp32 accumulate, tanhf: north_star FP32 bound "
                                       "(tests/test_gpu_tc3.py)"}),
     "tf32": dict(dtype="tf32", kernel="pinn::jet_tc_kernel<BWD, X3=false>", bound="tensor",
-                 tolerance={"loss_rel": 3e-3, "grad_rel_l2": 5e-3,
+                 tolerance={"loss_rel": 5e-3, "grad_rel_l2": 5e-3,
                             "mode": "tf32 operands, fp32 accumulate, tanh.approx (stated looser bound; "
                                     "tests/test_gpu_tc.py)"}),
     "fp32": dict(dtype="f32", kernel="pinn::jet_kernel", bound="fp32_fma",

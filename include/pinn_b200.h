@@ -136,6 +136,10 @@ int pinn_param_count(const pinn_desc_t* desc, int64_t* n_params);
  * per-CTA activation slabs); independent of n_points beyond a grid-size cap. */
 int pinn_workspace_bytes(const pinn_desc_t* desc, int64_t n_points, size_t* bytes);
 
+/* Same, for a workspace that will only ever be passed to pinn_jet_loss_fwd (want_grad == 0): no activation slabs.
+ * (DNN.forward in dnn.py:54-55 and physics.compute_gradient in physics.py:6-15 are forward-only passes.) */
+int pinn_workspace_bytes_ex(const pinn_desc_t* desc, int64_t n_points, int32_t want_grad, size_t* bytes);
+
 /*
  * Loss evaluation without gradient: jet forward + fused residual / misfit sums.
  * Replaces DNN.forward (dnn.py:54-55) + compute_gradient (physics.py:6-15) + the physics.py

@@ -69,6 +69,7 @@ SYMBOLS = {
     "pinn_last_error": (C.c_char_p, []),
     "pinn_param_count": (C.c_int, [C.POINTER(Desc), C.POINTER(C.c_int64)]),
     "pinn_workspace_bytes": (C.c_int, [C.POINTER(Desc), _I64, C.POINTER(C.c_size_t)]),
+    "pinn_workspace_bytes_ex": (C.c_int, [C.POINTER(Desc), _I64, _I32, C.POINTER(C.c_size_t)]),
     "pinn_jet_loss_fwd": (C.c_int, [C.POINTER(Desc), C.POINTER(EvalArgs), _P]),
     "pinn_jet_loss_fwdbwd": (C.c_int, [C.POINTER(Desc), C.POINTER(EvalArgs), _P]),
     "pinn_mask_count": (C.c_int, [C.POINTER(Desc), _P, _I64, _P, _P]),

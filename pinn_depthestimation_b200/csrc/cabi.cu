@@ -23,7 +23,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 // jet_fp32.cu
 int validate_desc(const pinn_desc_t* D);
-int workspace_bytes(const pinn_desc_t* D, long long n_points, size_t* bytes);
+int workspace_bytes(const pinn_desc_t* D, long long n_points, bool bwd, size_t* bytes);
 int run_pass(const pinn_desc_t* D, const pinn_eval_args_t* a, bool bwd, cudaStream_t st);
 int run_mask_count(const pinn_desc_t* D, const float* inputs, long long n, float* out, cudaStream_t st);
 int run_finalize(const pinn_desc_t* D, const double* s, const double* sb, long long n_fid, long long n_res,
@@ -59,7 +59,12 @@ int pinn_param_count(const pinn_desc_t* desc, int64_t* n_params) {
 
 int pinn_workspace_bytes(const pinn_desc_t* desc, int64_t n_points, size_t* bytes) {
   if (!bytes) return set_error("bytes is NULL"), PINN_E_ARG;
-  return workspace_bytes(desc, n_points, bytes);
+  return workspace_bytes(desc, n_points, true, bytes);
+}
+
+int pinn_workspace_bytes_ex(const pinn_desc_t* desc, int64_t n_points, int32_t want_grad, size_t* bytes) {
+  if (!bytes) return set_error("bytes is NULL"), PINN_E_ARG;
+  return workspace_bytes(desc, n_points, want_grad != 0, bytes);
 }
 
 int pinn_jet_loss_fwd(const pinn_desc_t* desc, const pinn_eval_args_t* args, void* stream) {

@@ -735,7 +735,7 @@ int make_config(const pinn_desc_t* D, bool bwd, Config* c) {
 
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
-int workspace_bytes(const pinn_desc_t* D, long long n_points, size_t* bytes) {
+int workspace_bytes(const pinn_desc_t* D, long long n_points, bool bwd, size_t* bytes) {
   Config c;
   int rc = validate_desc(D);
   if (rc) return rc;
@@ -752,7 +752,7 @@ int workspace_bytes(const pinn_desc_t* D, long long n_points, size_t* bytes) {
     *bytes = align256(pk) + align256(sl) + 256;
     return PINN_OK;
   }
-  rc = make_config(D, true, &c);
+  rc = make_config(D, bwd, &c);   // (forward-only: no activation slabs)
   if (rc) return rc;
   long long tiles = (n_points + c.TP - 1) / c.TP;
   long long grid = tiles < c.max_ctas ? tiles : c.max_ctas;

@@ -6,7 +6,8 @@ keys and pickling behaviour -- but forward/backward run on the sm_100a kernels t
 
 * `forward(x)` launches the value-only fused forward (pinn_jet_loss_fwd, residual kind NONE).
 * its autograd backward launches the fused forward+reverse with caller-supplied output seeds
-  (PINN_RES_EXTERNAL) and hands each nn.Parameter its slice of the flat gradient.
+  (PINN_RES_EXTERNAL) and hands each nn.Parameter its slice of the flat gradient; that node is separate
+  from the one that answers d out / d x, so input-only derivatives never pay for a weight gradient.
 * d out / d x (what physics.compute_gradient asks autograd for) is answered with forward jets, and
   is itself differentiable w.r.t. the weights (again through PINN_RES_EXTERNAL), so the reference's
   unmodified physics.py also runs on top of this module (3 input directions per jet launch).
@@ -51,23 +52,29 @@ def provenance(t):
 
 
 class _Runner:
-    """Caches descriptor + workspace for (kind, point count) of one module."""
+    """One descriptor + workspace per (kind, directions, point count, device, forward-only?) of one module.  The key
+    does NOT contain the input pointer: the reference's loss_func feeds a freshly `torch.cat`-ed tensor on every call
+    (train_newmethod.py:123-124), so the pass is re-pointed at the new storage instead of being rebuilt."""
 
     def __init__(self, module):
         self.module = module
-        self.cache = {}
+        self.cache = OrderedDict()
+        self.jet_losses = OrderedDict()   # physics.py facade: fused residual passes of this module
 
-    def get(self, kind, ext_dirs, inputs):
+    def get(self, kind, ext_dirs, inputs, want_grad=True):
         from .fused import _Pass
-        key = (kind, tuple(ext_dirs), inputs.data_ptr(), tuple(inputs.shape), inputs._version)
+        key = (kind, tuple(ext_dirs), tuple(inputs.shape), str(inputs.device), bool(want_grad))
         p = self.cache.get(key)
         if p is None:
-            if len(self.cache) > 8:
-                self.cache.clear()
+            while len(self.cache) >= 12:
+                self.cache.popitem(last=False)
             spec = PassSpec(layers=self.module.layer_sizes, activation=self.module.activation_name,
                             kind=kind, ext_dirs=list(ext_dirs))
-            p = _Pass(spec, inputs, None)
+            p = _Pass(spec, inputs, None, want_grad=want_grad)
             self.cache[key] = p
+        else:
+            self.cache.move_to_end(key)
+            p.rebind(inputs)
         return p
 
 
@@ -94,7 +101,7 @@ class _JetFunction(torch.autograd.Function):
         o = module.layer_sizes[-1]
         xin = x.detach().to(torch.float32).contiguous()
         flat = module.flat_params()
-        ps = module._runner.get("external", dirs, xin)
+        ps = module._runner.get("external", dirs, xin, want_grad=False)
         n = xin.shape[0]
         out = torch.empty(n, o, device=xin.device)
         douts = [torch.empty(n, o, device=xin.device) for _ in dirs]
@@ -121,49 +128,66 @@ class _JetFunction(torch.autograd.Function):
         return (None, None, None, *module.split_flat(grad))
 
 
-class _MLPFunction(torch.autograd.Function):
-    """Value-only forward; backward to the weights by the fused kernel, to the inputs by jets."""
+class _MLPValue(torch.autograd.Function):
+    """Value-only forward; its backward answers d out / d x with forward jets (differentiable w.r.t. the weights, so
+    physics.compute_gradient's create_graph=True works).  The weights are deliberately NOT inputs of this node: their
+    gradient hangs on the separate _MLPParamGrad node, so an `autograd.grad(pred, var)` w.r.t. the inputs only
+    (physics.py:6-15; 13 of them per Navier_Stokes call) never launches a weight-gradient sweep it would throw away."""
 
     @staticmethod
-    def forward(ctx, module, x, *params):
+    def forward(ctx, module, x):
         xin = x.detach().to(torch.float32).contiguous()
         flat = module.flat_params()
-        ps = module._runner.get("none", (), xin)
+        ps = module._runner.get("none", (), xin, want_grad=False)
         out = torch.empty(xin.shape[0], module.layer_sizes[-1], device=xin.device)
         a = ps.args(flat, None, 1, 1, 0, out=out)
         with torch.cuda.device(xin.device):
             _cabi.check(_cabi.lib().pinn_jet_loss_fwd(C.byref(ps.desc), C.byref(a), _stream(xin.device)),
                         "pinn_jet_loss_fwd")
-        ctx.module, ctx.x, ctx.params = module, x, params
+        ctx.module, ctx.x = module, x
         return out
 
     @staticmethod
     def backward(ctx, g_out):
         module, x = ctx.module, ctx.x
-        gx = None
-        if ctx.needs_input_grad[1]:
-            # vjp w.r.t. the inputs = sum_n g_out[:,n] * d out_n/d x_c, written with differentiable
-            # torch ops on the jet outputs so that create_graph=True (physics.compute_gradient) works
-            d = module.layer_sizes[0]
-            with torch.enable_grad():
-                cols = []
-                for c0 in range(0, d, _cabi.MAX_DIRS):      # <= 3 jet directions per launch
-                    dirs = tuple(range(c0, min(d, c0 + _cabi.MAX_DIRS)))
-                    jets = _JetFunction.apply(module, x, dirs, *ctx.params)
-                    cols += [(g_out * dj).sum(dim=1) for dj in jets[1:]]
-                gx = torch.stack(cols, dim=1).to(x.dtype)
-        gparams = [None] * len(ctx.params)
-        if any(ctx.needs_input_grad[2:]):
-            xin = x.detach().to(torch.float32).contiguous()
-            flat = module.flat_params()
-            ps = module._runner.get("external", (), xin)
-            grad = torch.empty_like(flat)
-            a = ps.args(flat, grad, 1, 1, 0, seed_out=g_out.detach().to(torch.float32).contiguous())
-            with torch.cuda.device(xin.device):
-                _cabi.check(_cabi.lib().pinn_jet_loss_fwdbwd(C.byref(ps.desc), C.byref(a),
-                                                             _stream(xin.device)), "pinn_jet_loss_fwdbwd")
-            gparams = module.split_flat(grad)
-        return (None, gx, *gparams)
+        if not ctx.needs_input_grad[1]:
+            return None, None
+        # vjp w.r.t. the inputs = sum_n g_out[:,n] * d out_n/d x_c, written with differentiable torch ops on the jet
+        # outputs so that create_graph=True works
+        d = module.layer_sizes[0]
+        params = tuple(module.parameters())
+        with torch.enable_grad():
+            cols = []
+            for c0 in range(0, d, _cabi.MAX_DIRS):      # <= 3 jet directions per launch
+                dirs = tuple(range(c0, min(d, c0 + _cabi.MAX_DIRS)))
+                jets = _JetFunction.apply(module, x, dirs, *params)
+                cols += [(g_out * dj).sum(dim=1) for dj in jets[1:]]
+            gx = torch.stack(cols, dim=1).to(x.dtype)
+        return None, gx
+
+
+class _MLPParamGrad(torch.autograd.Function):
+    """Zero-valued [N,o] tensor added to the network output; its backward is the weight gradient of the value path
+    (fused forward + reverse sweep with the caller's d loss / d out as external seeds)."""
+
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        ctx.module = module
+        ctx.xin = x.detach().to(torch.float32).contiguous()
+        return ctx.xin.new_zeros(ctx.xin.shape[0], module.layer_sizes[-1])
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_out):
+        module, xin = ctx.module, ctx.xin
+        flat = module.flat_params()
+        ps = module._runner.get("external", (), xin)
+        grad = torch.empty_like(flat)
+        a = ps.args(flat, grad, 1, 1, 0, seed_out=g_out.detach().to(torch.float32).contiguous())
+        with torch.cuda.device(xin.device):
+            _cabi.check(_cabi.lib().pinn_jet_loss_fwdbwd(C.byref(ps.desc), C.byref(a),
+                                                         _stream(xin.device)), "pinn_jet_loss_fwdbwd")
+        return (None, None, *module.split_flat(grad))
 
 
 class DNN(nn.Module):
@@ -254,6 +278,8 @@ class DNN(nn.Module):
 
     def forward(self, x):
         _check_input(self, x)
-        out = _MLPFunction.apply(self, x, *self.parameters())
+        out = _MLPValue.apply(self, x)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            out = out + _MLPParamGrad.apply(self, x, *self.parameters())
         _remember(out, self, x)
         return out

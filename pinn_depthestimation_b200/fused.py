@@ -34,13 +34,16 @@ def _dev_f32(t: torch.Tensor, name: str) -> torch.Tensor:
 class _Pass:
     """Buffers + descriptor of one pass over one point set."""
 
-    def __init__(self, spec: PassSpec, inputs: torch.Tensor, targets: Optional[torch.Tensor]):
+    def __init__(self, spec: PassSpec, inputs: torch.Tensor, targets: Optional[torch.Tensor],
+                 want_grad: bool = True):
         self.spec = spec
         self.desc = spec.to_desc()
+        self.want_grad = bool(want_grad)
         self.inputs = _dev_f32(inputs, "inputs")
         if self.inputs.dim() != 2 or self.inputs.shape[1] != spec.layers[0]:
             raise ValueError(f"inputs must be [N,{spec.layers[0]}], got {tuple(self.inputs.shape)}")
         self.n = int(self.inputs.shape[0])
+        self._mask_key = None
         self.targets = None
         if spec.target_cols:
             if targets is None:
@@ -52,8 +55,8 @@ class _Pass:
         lib = _cabi.lib()
         nbytes = C.c_size_t(0)
         with torch.cuda.device(dev):
-            _cabi.check(lib.pinn_workspace_bytes(C.byref(self.desc), self.n, C.byref(nbytes)),
-                        "pinn_workspace_bytes")
+            _cabi.check(lib.pinn_workspace_bytes_ex(C.byref(self.desc), self.n, 1 if self.want_grad else 0,
+                                                    C.byref(nbytes)), "pinn_workspace_bytes_ex")
         self.workspace = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=dev)
         off = (-self.workspace.data_ptr()) % 256
         self._ws_ptr = self.workspace.data_ptr() + off
@@ -62,11 +65,33 @@ class _Pass:
         self.mask_count = None
         if spec.kind == "continuity_only":
             self.mask_count = torch.zeros(1, dtype=torch.float32, device=dev)
-            st = torch.cuda.current_stream(dev).cuda_stream
-            with torch.cuda.device(dev):
-                _cabi.check(lib.pinn_mask_count(C.byref(self.desc), _cabi.ptr(self.inputs), self.n,
-                                                _cabi.ptr(self.mask_count), C.c_void_p(st)),
-                            "pinn_mask_count")
+            self._count_mask()
+
+    def _count_mask(self):
+        """#{x < 25.5} of the current inputs (physics.py:27) -> self.mask_count (this rank's points only)."""
+        dev = self.inputs.device
+        st = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _cabi.check(_cabi.lib().pinn_mask_count(C.byref(self.desc), _cabi.ptr(self.inputs), self.n,
+                                                    _cabi.ptr(self.mask_count), C.c_void_p(st)),
+                        "pinn_mask_count")
+        self._mask_key = (self.inputs.data_ptr(), self.inputs._version)
+
+    def rebind(self, inputs: torch.Tensor, targets: Optional[torch.Tensor] = None):
+        """Point this pass at another [N,d] input tensor of the same shape (the reference's loss_func builds a fresh
+        `torch.cat` of its input columns on every call): descriptor, workspace and sums are kept, only the pointers
+        change; the mask count is redone when the tensor (or its version) differs from the one it was counted on."""
+        inputs = _dev_f32(inputs, "inputs")
+        if tuple(inputs.shape) != tuple(self.inputs.shape) or inputs.device != self.inputs.device:
+            raise ValueError("rebind: inputs must keep their shape and device")
+        self.inputs = inputs
+        if targets is not None:
+            targets = _dev_f32(targets, "targets")
+            if self.targets is None or tuple(targets.shape) != tuple(self.targets.shape):
+                raise ValueError("rebind: targets must keep their shape")
+            self.targets = targets
+        if self.mask_count is not None and self._mask_key != (inputs.data_ptr(), inputs._version):
+            self._count_mask()
 
     def args(self, params, grad, n_res_global, n_fid_global, flags, out=None, douts=None,
              seed_out=None, seed_douts=None):

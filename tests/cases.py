@@ -9,7 +9,8 @@ from oracle import jet_oracle as jo
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 NAN = ["cmb_nan"]            # the reference's loss is NaN by construction (physics.py:106-108 with k == 0)
-ALL = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f[:-4] not in NAN)
+ALL = sorted(f[:-4] for f in os.listdir(GOLDEN)
+             if f.endswith(".npz") and f[:-4] not in NAN and not f.startswith(("curve_", "ref_")))
 SMALL = [n for n in ALL if not n.startswith("wide")]
 
 
