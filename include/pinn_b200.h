@@ -195,6 +195,23 @@ int pinn_adam_step(float* params, const float* grad, float* exp_avg, float* exp_
                    int64_t n, float lr_host, float beta1, float beta2, float eps,
                    float weight_decay, int64_t step_count, void* stream);
 
+/* ---- one-off data path on the device (train_newmethod.py:226-255, train.py:203-276, operations.py:4-30) ---- */
+
+/* out2 = [nanmin(x), nanmax(x)] (operations.py:26-29: ranges of every input variable other than x / y). */
+int pinn_nan_minmax(const float* x, int64_t n, float* out2, void* stream);
+
+/*
+ * Normalise, hstack and NaN-filter in one pass: cols_host is a HOST array of n_in + n_true DEVICE column pointers
+ * (each [n]); input column c is mapped to 2 (x - lo[c]) / (hi[c] - lo[c]) - 1 (all zeros when hi == lo,
+ * operations.py:4-7) and written to inputs_out [n_kept, n_in]; the true columns go to trues_out [n_kept, n_true]
+ * unchanged.  Rows are dropped, order preserved, when they hold a NaN in a true column (nan_policy & 1,
+ * train_newmethod.py:252-255) and / or in an input column (nan_policy & 2, train.py:274-276).  n_kept: device int64.
+ * scratch: >= ceil(n / 256) int32.  lo_host / hi_host: host arrays [n_in].
+ */
+int pinn_assemble_points(const float* const* cols_host, int32_t n_in, int32_t n_true, const float* lo_host,
+                         const float* hi_host, int32_t nan_policy, int64_t n, float* inputs_out, float* trues_out,
+                         int64_t* n_kept, int32_t* scratch, void* stream);
+
 /* Measurement helper (bench.py): launches an FP32-FMA-bound kernel of `ctas` x 256 threads and
  * reports the FLOPs it executes in *flops_out (host); time it with events on `stream`. */
 int pinn_fma_probe(float* out, int32_t iters, int32_t ctas, double* flops_out, void* stream);

@@ -78,6 +78,9 @@ SYMBOLS = {
     "pinn_vec_stats": (C.c_int, [_P, _P, _I64, _P, _P]),
     "pinn_axpy": (C.c_int, [_F, _P, _P, _I64, _P]),
     "pinn_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I64, _P]),
+    "pinn_nan_minmax": (C.c_int, [_P, _I64, _P, _P]),
+    "pinn_assemble_points": (C.c_int, [C.POINTER(C.c_void_p), _I32, _I32, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                       _I32, _I64, _P, _P, _P, _P, _P]),
     "pinn_fma_probe": (C.c_int, [_P, _I32, _I32, C.POINTER(C.c_double), _P]),
 }
 

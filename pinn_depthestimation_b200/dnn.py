@@ -261,12 +261,12 @@ class DNN(nn.Module):
                     break
                 o += p.numel()
         if not ok:
-            flat = torch.cat([p.detach().to(torch.float32).reshape(-1) for p in ps]).contiguous()
-            o = 0
+            # adopts the buffer when an optimiser has already flattened the parameters (lbfgs.flatten_params is idempotent)
+            from .lbfgs import flatten_params
             for p in ps:
-                p.data = flat[o:o + p.numel()].view_as(p)
-                o += p.numel()
-            self._flat = flat
+                if p.dtype != torch.float32:
+                    p.data = p.data.to(torch.float32)
+            self._flat = flatten_params(ps, allow_cpu=True)
         return self._flat
 
     def split_flat(self, vec):

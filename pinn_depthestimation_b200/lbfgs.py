@@ -140,14 +140,15 @@ def strong_wolfe(evaluate, clone, t, f, g, gtd, d_norm, c1=1e-4, c2=0.9, toleran
 # ------------------------------------------------------------------------------------------------
 # flat parameter plumbing shared by LBFGS and FusedAdam
 # ------------------------------------------------------------------------------------------------
-def flatten_params(params):
-    """Make every parameter a view into ONE flat fp32 CUDA buffer (parameters() order) and return it.
-    Idempotent: parameters that already are consecutive views of one buffer are left alone."""
+def flatten_params(params, allow_cpu=False):
+    """Make every parameter a view into ONE flat fp32 buffer (parameters() order) and return it.
+    Idempotent: parameters that already are consecutive views of one buffer are left alone, so the DNN facade,
+    LBFGS, FusedAdam and LBFGSBOptimizer all end up sharing the same flat vector whichever comes first."""
     params = list(params)
     if not params:
         raise ValueError("optimizer got an empty parameter list")
     for p in params:
-        if not p.is_cuda:
+        if not p.is_cuda and not allow_cpu:
             raise RuntimeError("pinn_b200 optimisers need CUDA parameters: no CPU fallback")
         if p.dtype != torch.float32:
             raise TypeError("pinn_b200 optimisers need float32 parameters")

@@ -42,10 +42,12 @@ class FusedClosure:
 class pinn:
     def __init__(self, config, data_input, data_true, residual="continuity_only",
                  fid_input=None, fid_true=None, device=None, log_dir=None, group=None,
-                 log_every=1000, precision="fp32"):
+                 log_every=1000, precision="fp32", dump_at=50000, dump_path='data_at50k.mat'):
         """data_input [N,d] / data_true [N,n_true]: numpy arrays exactly as the reference's
-        __main__ builds them (train_newmethod.py:226-255).  When fid_input/fid_true are given the
-        train.py form is used: data misfit on (fid_input, fid_true), residual on data_input."""
+        __main__ builds them (train_newmethod.py:226-255), or device tensors from data.assemble_points.
+        When fid_input/fid_true are given the train.py form is used: data misfit on (fid_input, fid_true),
+        residual on data_input.  dump_at / dump_path: the prediction dump of train_newmethod.py:141-153
+        (`data_at50k.mat`, written by the evaluation that starts with iter == 50000)."""
         self.config = config
         lay = config['layers']
         self.layers = [lay['input_features']] + [lay['hidden_width']] * lay['hidden_layers'] \
@@ -66,8 +68,13 @@ class pinn:
         self._ring_n = 0
         self.history = []                 # flushed (iter, fid, res, total)
 
+        self.dump_at, self.dump_path, self.group = dump_at, dump_path, group
         names_d, names_f = DIR_ORDER[residual], FIELD_ORDER[residual]
-        t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).to(self.device)
+
+        def t(a):
+            if isinstance(a, torch.Tensor):
+                return a.to(device=self.device, dtype=torch.float32).contiguous()
+            return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).to(self.device)
         if fid_input is None:
             # train_newmethod.py form: inputs in config['data']['inputs'] order, outputs =
             # trues followed by unknowns (train_newmethod.py:136-139)
@@ -80,11 +87,14 @@ class pinn:
                             target_cols=list(range(n_true)), w_fid=self.weight_fidelity,
                             w_res=self.weight_residual, precision=precision)
             self.jl = JetLoss(spec, t(data_input), t(data_true), group=group)
+            self.out_names = out_names
         else:
             in_names = list(config['data_residual']['inputs'].keys())
             out_names = list(config['data_residual']['outputs'])
             fid_out = list(config['data_fidelity']['outputs'])
-            tw = [config['loss'][f'weight_{k}_loss'] for k in fid_out]
+            # per-output weights (train.py:94-95); config.json / config_txyz.json do not carry them: 1
+            tw = [config['loss'].get(f'weight_{k}_loss', 1) for k in fid_out]
+            self.out_names = out_names
             common = dict(layers=self.layers, activation=self.dnn.activation_name,
                           w_fid=self.weight_fidelity, w_res=self.weight_residual, precision=precision)
             sres = PassSpec(kind=residual, dirs={n: in_names.index(n) for n in names_d},
@@ -108,7 +118,39 @@ class pinn:
             line_search_fn=l['line_search_fn'])
 
     # ---- one evaluation: loss parts on device + flat gradient; bookkeeping of loss_func ----------
+    def predictions(self, flat=None):
+        """Network outputs [N, o] at the residual points (this rank's shard), value-only fused forward."""
+        flat = self.flat if flat is None else flat
+        out = torch.empty(self.jl.res.n, self.layers[-1], dtype=torch.float32, device=self.device)
+        self.jl.loss(flat, out=out)
+        return out
+
+    def dump_predictions(self, path, flat=None):
+        """train_newmethod.py:141-153: {'pred_<name>': [N,1] float32} for the true and unknown variables -> .mat"""
+        out = self.predictions(flat)
+        if self.group is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(self.group)
+            sizes = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in range(world)]
+            dist.all_gather(sizes, torch.tensor([out.shape[0]], dtype=torch.int64, device=self.device), group=self.group)
+            nmax = int(max(s.item() for s in sizes))
+            pad = torch.zeros(nmax, out.shape[1], device=self.device)
+            pad[:out.shape[0]] = out
+            allp = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(allp, pad, group=self.group)
+            out = torch.cat([a[:int(s.item())] for a, s in zip(allp, sizes)])
+            if dist.get_rank(self.group) != 0:
+                return None
+        import scipy.io as sio
+        host = out.cpu().numpy()
+        data = {f'pred_{k}': host[:, i:i + 1].copy() for i, k in enumerate(self.out_names)}
+        sio.savemat(path, data)
+        print(f'Data saved to {path} after {self.iter:,} iterations.')
+        return data
+
     def _evaluate(self, flat, grad):
+        if self.dump_at is not None and self.iter == self.dump_at:   # before the counter moves, like the reference
+            self.dump_predictions(self.dump_path, flat)
         parts = self.jl.loss_and_grad(flat, grad)
         self.iter += 1
         self._ring[self._ring_n].copy_(parts)
