@@ -183,6 +183,37 @@ int pinn_lbfgs_direction(const float* hist_s, const float* hist_y, const float* 
                          int32_t m_used, int32_t head, int64_t n_params, float* scratch,
                          void* stream);
 
+/*
+ * Device-resident torch.optim.LBFGS.step (torch/optim/lbfgs.py:333-537 with _strong_wolfe :40-209 and
+ * _cubic_interpolate :12-37; reference call sites train_newmethod.py:108-117,204-209).  The host only launches the
+ * closure's evaluation and then pinn_lbfgs_advance, which performs everything up to the next evaluation in ONE
+ * cluster kernel (line-search transition, gradient clones, termination tests, curvature-pair update, two-loop
+ * recursion, first step length, next trial point written into flat_params) and copies a small status block to
+ * status_host.  One stream synchronisation per evaluation, no other host round trips.
+ */
+typedef struct pinn_lbfgs_cfg {
+  double lr, tolerance_grad, tolerance_change;
+  int32_t max_iter, max_eval, history_size;
+} pinn_lbfgs_cfg_t;
+
+typedef struct pinn_lbfgs_status {
+  int32_t code;             /* 1 = evaluate the closure at flat_params again, 2 = step() is over */
+  int32_t n_iter;           /* iterations of this step() call                                          */
+  int32_t current_evals;    /* evaluations of this step() call                                         */
+  int32_t n_iter_total;     /* state['n_iter']                                                         */
+  int32_t func_evals_total; /* state['func_evals']                                                     */
+  int32_t phase, history_used, pad;
+  double t, loss, first_loss, gtd, d_norm;
+} pinn_lbfgs_status_t;
+
+int pinn_lbfgs_workspace_bytes(int64_t n_params, int32_t history_size, size_t* bytes);
+/* Start of a step() call.  reset != 0 also clears the history and the counters (a new optimiser). */
+int pinn_lbfgs_begin(void* workspace, int64_t n_params, const pinn_lbfgs_cfg_t* cfg, int32_t reset, void* stream);
+/* grad / *loss: gradient and loss (device) of the evaluation at the current flat_params.  status_host: HOST memory
+ * (pinned), filled by an async copy on `stream`: synchronise the stream before reading it. */
+int pinn_lbfgs_advance(void* workspace, int64_t n_params, int32_t history_size, float* flat_params, float* grad,
+                       const float* loss, void* status_host, void* stream);
+
 /* out6 = [a.b, sum|a|, max|a|, max|b|, a.a, b.b]  (b may be NULL; one cluster launch, deterministic) */
 int pinn_vec_stats(const float* a, const float* b, int64_t n, float* out6, void* stream);
 

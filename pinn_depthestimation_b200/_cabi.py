@@ -59,6 +59,18 @@ class EvalArgs(C.Structure):
     ]
 
 
+class LbfgsCfg(C.Structure):
+    _fields_ = [("lr", C.c_double), ("tolerance_grad", C.c_double), ("tolerance_change", C.c_double),
+                ("max_iter", C.c_int32), ("max_eval", C.c_int32), ("history_size", C.c_int32)]
+
+
+class LbfgsStatus(C.Structure):
+    _fields_ = [("code", C.c_int32), ("n_iter", C.c_int32), ("current_evals", C.c_int32), ("n_iter_total", C.c_int32),
+                ("func_evals_total", C.c_int32), ("phase", C.c_int32), ("history_used", C.c_int32), ("pad", C.c_int32),
+                ("t", C.c_double), ("loss", C.c_double), ("first_loss", C.c_double), ("gtd", C.c_double),
+                ("d_norm", C.c_double)]
+
+
 # PINN_B200_LIB selects another build of the same library (e.g. the -DPINN_TC_DEBUG cycle-counter build)
 LIB_PATH = os.environ.get("PINN_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpinn_b200.so")
 
@@ -75,6 +87,9 @@ SYMBOLS = {
     "pinn_mask_count": (C.c_int, [C.POINTER(Desc), _P, _I64, _P, _P]),
     "pinn_loss_finalize": (C.c_int, [C.POINTER(Desc), _P, _P, _I64, _I64, _P, _P, _P]),
     "pinn_lbfgs_direction": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I64, _P, _P]),
+    "pinn_lbfgs_workspace_bytes": (C.c_int, [_I64, _I32, C.POINTER(C.c_size_t)]),
+    "pinn_lbfgs_begin": (C.c_int, [_P, _I64, C.POINTER(LbfgsCfg), _I32, _P]),
+    "pinn_lbfgs_advance": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _P]),
     "pinn_vec_stats": (C.c_int, [_P, _P, _I64, _P, _P]),
     "pinn_axpy": (C.c_int, [_F, _P, _P, _I64, _P]),
     "pinn_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I64, _P]),

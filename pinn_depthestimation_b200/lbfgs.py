@@ -9,8 +9,14 @@ bracket + zoom) and :333-537 (`step`), restated branch for branch:
   `hist_s/hist_y [history_size, P]` (pinn_lbfgs_direction) instead of 2m host-synchronising dots;
 * g.d, sum|g|, max|g|, max|d|, y.s, y.y come from one deterministic cluster reduction
   (pinn_vec_stats); `params = x0 + t*d` is one launch on the flat parameter vector;
-* the scalar line-search logic runs on the host in float64 on those reductions: one small
-  device->host copy per closure evaluation (+ two per outer iteration), nothing else syncs.
+* with line_search_fn='strong_wolfe' (every reference config) the whole optimiser state machine between two
+  closure evaluations -- strong-Wolfe bracket / zoom transition, the gradient clones, termination tests,
+  curvature-pair update, two-loop recursion, step length, next trial point -- is ONE cluster kernel
+  (pinn_lbfgs_advance, csrc/lbfgs_dev.cu): the host launches the closure, then that kernel, and reads one small
+  status block (one stream synchronisation per evaluation);
+* the same logic is kept here as host code (`strong_wolfe`, `cubic_interpolate`, `LBFGS._step_host`): it serves
+  line_search_fn=None, is unit-tested on CPU against torch's own private functions, and is the yardstick the
+  device state machine is compared with (tests/test_gpu_optim.py).
 
 `step(closure)` accepts the reference's closure (zero_grad -> loss_func -> backward -> return
 loss).  A closure object that also has `flat_loss_and_grad(flat_params, flat_grad) -> parts`
@@ -231,6 +237,8 @@ class LBFGS(torch.optim.Optimizer):
         self._params = self.param_groups[0]["params"]
         self._flat = None
         self._bufs = None
+        self._dev = None
+        self.device_line_search = True    # False: keep the scalar logic on the host (tests compare the two)
 
     # ---- buffers --------------------------------------------------------------------------------
     def _setup(self):
@@ -272,8 +280,79 @@ class LBFGS(torch.optim.Optimizer):
                 _cabi.ptr(b["g"]), _cabi.ptr(b["d"]), m, b["used"], b["head"], self._flat.numel(),
                 _cabi.ptr(b["scratch"]), _stream(self._flat.device)), "pinn_lbfgs_direction")
 
+    # ---- device-resident state machine -------------------------------------------------------------
+    def _setup_device(self):
+        flat = flatten_params(self._params)
+        m = int(self.param_groups[0]["history_size"])
+        if self._dev is None or self._dev["flat_ptr"] != flat.data_ptr() or self._dev["m"] != m:
+            lib = _cabi.lib()
+            nbytes = C.c_size_t(0)
+            _cabi.check(lib.pinn_lbfgs_workspace_bytes(flat.numel(), m, C.byref(nbytes)), "pinn_lbfgs_workspace_bytes")
+            ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=flat.device)
+            off = (-ws.data_ptr()) % 256
+            self._dev = dict(flat_ptr=flat.data_ptr(), m=m, ws=ws, ws_ptr=ws.data_ptr() + off, fresh=True,
+                             g=torch.zeros_like(flat),
+                             status=torch.zeros(C.sizeof(_cabi.LbfgsStatus), dtype=torch.uint8).pin_memory())
+        self._flat = flat
+        return flat
+
+    def _evaluate_into(self, closure, g):
+        """closure -> device loss scalar [1]; the flat gradient lands in g."""
+        fl = getattr(closure, "flat_loss_and_grad", None)
+        if fl is not None:
+            return fl(self._flat, g)[2:3]
+        with torch.enable_grad():
+            loss = closure()
+        views = [p.grad.reshape(-1) if p.grad is not None else p.new_zeros(p.numel()) for p in self._params]
+        torch.cat(views, 0, out=g)
+        return loss.detach().reshape(1).to(torch.float32)
+
+    def _step_device(self, closure):
+        group = self.param_groups[0]
+        flat = self._setup_device()
+        dv, lib, dev = self._dev, _cabi.lib(), flat.device
+        state = self.state[self._params[0]]
+        state.setdefault("func_evals", 0)
+        state.setdefault("n_iter", 0)
+        cfg = _cabi.LbfgsCfg(float(group["lr"]), float(group["tolerance_grad"]), float(group["tolerance_change"]),
+                             int(group["max_iter"]), int(group["max_eval"]), dv["m"])
+        with torch.cuda.device(dev):
+            _cabi.check(lib.pinn_lbfgs_begin(C.c_void_p(dv["ws_ptr"]), flat.numel(), C.byref(cfg),
+                                             1 if dv["fresh"] else 0, _stream(dev)), "pinn_lbfgs_begin")
+        dv["fresh"] = False
+        stream = torch.cuda.current_stream(dev)
+        status = _cabi.LbfgsStatus.from_buffer(dv["status"].numpy())
+        orig_loss = None
+        while True:
+            loss = self._evaluate_into(closure, dv["g"])
+            if orig_loss is None:
+                orig_loss = loss.clone()
+            if loss.dtype != torch.float32 or not loss.is_cuda:
+                loss = loss.to(device=dev, dtype=torch.float32)
+            with torch.cuda.device(dev):
+                _cabi.check(lib.pinn_lbfgs_advance(C.c_void_p(dv["ws_ptr"]), flat.numel(), dv["m"], _cabi.ptr(flat),
+                                                   _cabi.ptr(dv["g"]), _cabi.ptr(loss),
+                                                   C.c_void_p(dv["status"].data_ptr()), _stream(dev)),
+                            "pinn_lbfgs_advance")
+            stream.synchronize()                      # the one host round trip per evaluation
+            if status.code != 1:
+                break
+        if status.code != 2:
+            raise RuntimeError(f"pinn_lbfgs_advance returned status {status.code}")
+        state["n_iter"] = int(status.n_iter_total)
+        state["func_evals"] = int(status.func_evals_total)
+        state["t"], state["loss"] = float(status.t), float(status.loss)
+        state["history_used"] = int(status.history_used)
+        return orig_loss.reshape(())
+
     @torch.no_grad()
     def step(self, closure):
+        if self.param_groups[0]["line_search_fn"] == "strong_wolfe" and self.device_line_search:
+            return self._step_device(closure)
+        return self._step_host(closure)
+
+    @torch.no_grad()
+    def _step_host(self, closure):
         group = self.param_groups[0]
         lr = float(group["lr"])
         max_iter, max_eval = group["max_iter"], group["max_eval"]

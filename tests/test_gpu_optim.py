@@ -279,3 +279,43 @@ def test_train_main_script_runs_a_reference_style_config(tmp_path):
     assert (tmp_path / "log" / "model.pth").exists()
     assert (tmp_path / "log" / "log.txt").exists()
     assert model.history[-1][3] < model.history[0][3]
+
+
+@pytest.mark.parametrize("name,max_iter,max_eval", [("cmb_h_small", 60, 75), ("txyz", 40, 50), ("ftemp_small", 80, 100),
+                                                    ("cmb_h_small", 30, 17), ("ragged", 25, 31)])
+def test_device_line_search_takes_the_same_branches_as_the_host_restatement(name, max_iter, max_eval):
+    """The cluster-kernel state machine (csrc/lbfgs_dev.cu) against the host restatement of torch's step / _strong_wolfe
+    (LBFGS._step_host, itself held to torch's private functions on CPU): same evaluation points, so identical iteration
+    and evaluation counts and the same loss curve, over bracket, zoom and max_eval exits and across two step() calls."""
+    from pinn_depthestimation_b200.lbfgs import LBFGS
+    dev = torch.device("cuda:0")
+    case, flat, X, T, jl = _setup_problem(name, dev)
+    kw = dict(lr=1, max_iter=max_iter, max_eval=max_eval, history_size=7, tolerance_grad=0.0, tolerance_change=0.0,
+              line_search_fn="strong_wolfe")
+    runs = {}
+    for device_ls in (False, True):
+        p = torch.nn.Parameter(torch.from_numpy(flat.copy()).to(dev))
+        opt = LBFGS([p], **kw)
+        opt.device_line_search = device_ls
+        curve = []
+
+        class Closure:
+            def flat_loss_and_grad(self, fp, fg):
+                parts = jl.loss_and_grad(fp, fg)
+                curve.append(parts[2].item())
+                return parts
+        first = opt.step(Closure())
+        n1 = (opt.state[p]["n_iter"], opt.state[p]["func_evals"])
+        opt.step(Closure())          # history and the step length carry over (torch keeps them in self.state)
+        st = opt.state[p]
+        runs[device_ls] = (float(first), n1, st["n_iter"], st["func_evals"], np.array(curve), p.detach().cpu().numpy())
+    h, d = runs[False], runs[True]
+    print(f"{name}: host {h[1]} -> ({h[2]}, {h[3]}), device {d[1]} -> ({d[2]}, {d[3]}); loss {h[4][0]:.4e} -> {h[4][-1]:.4e}")
+    assert d[0] == h[0]
+    assert d[1] == h[1] and d[2] == h[2] and d[3] == h[3]
+    assert len(d[4]) == len(h[4])
+    # same evaluation points up to float atomics in the gradient kernel (1e-7 noise that the search can amplify late)
+    k = min(20, len(h[4]))
+    assert np.max(np.abs(d[4][:k] - h[4][:k]) / np.abs(h[4][:k])) <= 1e-4
+    assert abs(d[4][-1] - h[4][-1]) <= 2e-2 * abs(h[4][-1])
+    assert h[4][-1] < h[4][0]
