@@ -367,7 +367,7 @@ class LBFGS(torch.optim.Optimizer):
         state.setdefault("func_evals", 0)
         state.setdefault("n_iter", 0)
 
-        orig_loss = self._evaluate(closure)
+        orig_loss = self._evaluate(closure).detach().clone()   # (a flat closure returns a view of a reused device buffer)
         st = vec.read_stats(b["g"], b["d"], extra=orig_loss)
         loss = st[6]
         current_evals = 1

@@ -311,7 +311,7 @@ def test_device_line_search_takes_the_same_branches_as_the_host_restatement(name
         runs[device_ls] = (float(first), n1, st["n_iter"], st["func_evals"], np.array(curve), p.detach().cpu().numpy())
     h, d = runs[False], runs[True]
     print(f"{name}: host {h[1]} -> ({h[2]}, {h[3]}), device {d[1]} -> ({d[2]}, {d[3]}); loss {h[4][0]:.4e} -> {h[4][-1]:.4e}")
-    assert d[0] == h[0]
+    assert d[0] == h[0] == h[4][0]           # step() returns the FIRST evaluation's loss (torch's orig_loss)
     assert d[1] == h[1] and d[2] == h[2] and d[3] == h[3]
     assert len(d[4]) == len(h[4])
     # same evaluation points up to float atomics in the gradient kernel (1e-7 noise that the search can amplify late)
