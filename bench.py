@@ -505,6 +505,37 @@ def main():
         lbfgs_side["n_points"] = n_total
         lbfgs_side["precision"] = args.precision
 
+    # ---- L-BFGS direction ("HBM-bound, reported as GB/s"): the two whole-chip passes over a full history ----
+    def direction_probe(n_par, m):
+        al = lambda x: (x + 255) & ~255
+        nb = C.c_size_t(0)
+        _cabi.check(lib.pinn_lbfgs_workspace_bytes(n_par, m, C.byref(nb)))
+        ws = torch.zeros(nb.value + 256, dtype=torch.uint8, device=dev)
+        off = (-ws.data_ptr()) % 256
+        tail = 6 * al(4 * n_par) + 2 * al((m + 1) * n_par * 4)          # the [P] vectors and the (s, y) ring
+        ws[off + nb.value - tail: off + nb.value].view(torch.float32).normal_(0.0, 1e-3)
+        gvec = torch.randn(n_par, device=dev) * 1e-3
+        byts = C.c_double(0)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        best = None
+        for _ in range(4):
+            e0.record()
+            _cabi.check(lib.pinn_lbfgs_direction_probe(C.c_void_p(ws.data_ptr() + off), n_par, m, _cabi.ptr(gvec),
+                                                       C.byref(byts), st))
+            e1.record()
+            torch.cuda.synchronize()
+            ms_ = e0.elapsed_time(e1)
+            best = ms_ if best is None else min(best, ms_)
+        return {"n_params": n_par, "history_size": m, "ms": best, "algorithmic_bytes": byts.value,
+                "gb_per_s": byts.value / (best * 1e-3) / 1e9,
+                "hbm_peak_gb_per_s": peaks.get("hbm_gbs"),
+                "note": "two streaming passes over the 2 m P history (dots with s, y, g; d = sum delta_j b_j) + the "
+                        "coefficient-space two-loop in the last CTA; at P = 41,703 the history is L2-resident"}
+
+    lbfgs_direction = None
+    if rank == 0 and args.lbfgs_iters > 0:
+        lbfgs_direction = [direction_probe(P, 100), direction_probe(41703, 100)]
+
     # ---- side measurement: the reference's own config shapes (latency + launch count) ----
     real_shapes, lbfgs_real = None, None
     if rank == 0 and args.real_shapes:
@@ -584,6 +615,7 @@ def main():
             "modes": modes,
             "lbfgs": lbfgs_side,
             "lbfgs_real_shape": lbfgs_real,
+            "lbfgs_direction": lbfgs_direction,
             "real_shapes_fp32": real_shapes,
             "strong_scaling_rows": scaling_rows,
         }

@@ -214,6 +214,12 @@ int pinn_lbfgs_begin(void* workspace, int64_t n_params, const pinn_lbfgs_cfg_t* 
 int pinn_lbfgs_advance(void* workspace, int64_t n_params, int32_t history_size, float* flat_params, float* grad,
                        const float* loss, void* status_host, void* stream);
 
+/* Measurement hook (bench.py): the two whole-chip passes of one direction computation over a FULL history of
+ * history_size pairs in `workspace` (a pinn_lbfgs_workspace_bytes buffer the caller filled with anything finite);
+ * *bytes_out (host) = the algorithmic bytes they move.  Time it with events on `stream`. */
+int pinn_lbfgs_direction_probe(void* workspace, int64_t n_params, int32_t history_size, const float* grad,
+                               double* bytes_out, void* stream);
+
 /* out6 = [a.b, sum|a|, max|a|, max|b|, a.a, b.b]  (b may be NULL; one cluster launch, deterministic) */
 int pinn_vec_stats(const float* a, const float* b, int64_t n, float* out6, void* stream);
 

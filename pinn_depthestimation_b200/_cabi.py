@@ -90,6 +90,7 @@ SYMBOLS = {
     "pinn_lbfgs_workspace_bytes": (C.c_int, [_I64, _I32, C.POINTER(C.c_size_t)]),
     "pinn_lbfgs_begin": (C.c_int, [_P, _I64, C.POINTER(LbfgsCfg), _I32, _P]),
     "pinn_lbfgs_advance": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _P]),
+    "pinn_lbfgs_direction_probe": (C.c_int, [_P, _I64, _I32, _P, C.POINTER(C.c_double), _P]),
     "pinn_vec_stats": (C.c_int, [_P, _P, _I64, _P, _P]),
     "pinn_axpy": (C.c_int, [_F, _P, _P, _I64, _P]),
     "pinn_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I64, _P]),

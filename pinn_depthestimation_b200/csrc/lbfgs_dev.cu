@@ -3,16 +3,33 @@
 // Everything torch.optim.LBFGS.step does between two closure evaluations -- the strong-Wolfe bracket / zoom transition
 // (torch/optim/lbfgs.py:40-209, cubic interpolation :12-37), the clones of the gradient it keeps for the bracket ends,
 // the end-of-iteration termination tests (:511-526), the curvature-pair update (:404-421), the two-loop recursion
-// (:432-447), the first step length (:454-457) and the next trial point x0 + t d -- is ONE launch of an 8-CTA thread-block
-// cluster (`lbfgs_advance_kernel`).  The host launches the closure's kernels, then this kernel, then reads ONE small status
-// block (one sync per evaluation) that only says "evaluate again" or "finished".  Call sites in the reference:
-// train_newmethod.py:108-117 (construction), :204-209 (the single step(closure) call with max_iter = 50000).
+// (:432-447), the first step length (:454-457) and the next trial point x0 + t d -- runs as a fixed sequence of four
+// launches per evaluation with all decisions taken on the device (`pinn_lbfgs_advance`).  The host launches the closure's
+// kernels, then these, then reads ONE small status block (one sync per evaluation) that only says "evaluate again" or
+// "finished".  Call sites in the reference: train_newmethod.py:108-117 (construction), :204-209 (the single step(closure)
+// call with max_iter = 50000).
 //
-// All scalar decisions are taken in double precision by thread 0 of every CTA from the same cluster-reduced inputs
-// (fixed summation order), so every CTA -- and every GPU of a sharded run, which all-reduce loss and gradient first --
-// takes the same branch.  pinn_depthestimation_b200/lbfgs.py holds the same logic as host code (used for
-// line_search_fn=None and as the CPU-tested restatement of torch's functions); tests/test_gpu_optim.py holds both to
-// torch's iteration / evaluation counts.
+//   1. lbfgs_advance_kernel   8-CTA cluster: line-search transition, gradient clones, termination tests; either writes the
+//                             next trial point of the running line search or raises `begin` (a new outer iteration starts)
+//   2. vl_dots_kernel         whole chip, only if `begin`: writes the candidate pair (s, y) into its ring slot and takes, in
+//                             ONE streaming pass over the history, the dot products of every stored vector with s, y and g;
+//                             the last CTA to finish (fixed-order reduction of the per-CTA partials) accepts the pair
+//                             (y.s > 1e-10), updates the Gram matrices S^T S, S^T Y, Y^T Y and runs the TWO-LOOP RECURSION IN
+//                             COEFFICIENT SPACE: d = sum_j delta_j b_j over the basis {s_i, y_i, g}, every s_i.q / y_i.r of
+//                             torch's loops being a (2m+1)-term sum over Gram entries in double precision -- the 2m dependent
+//                             vector passes of the textbook recursion (2m cluster barriers, 0.6 ms at m = 100 however small
+//                             the vectors are) collapse into one block-local scalar loop
+//   3. vl_combine_kernel      whole chip, only if `begin`: d = sum_j delta_j b_j (the second and last pass over the history),
+//                             prev_g = g, partial g.d / |g|_1 / max|d|; the last CTA forms the step length, tests
+//                             g.d > -tolerance_change and sets up the line search
+//   4. lbfgs_trial_kernel     whole chip, only if a line search starts: x0 = x, g_prev = g, x = x0 + t d
+// Traffic per outer iteration: two passes over the 2 m P history (HBM / L2 bound, no dependent chain) instead of two
+// passes broken into 2m barrier-separated steps on 8 SMs.
+//
+// All scalar decisions are taken in double precision from reductions with a fixed summation order, so every GPU of a
+// sharded run (which all-reduce loss and gradient first) takes the same branch.  pinn_depthestimation_b200/lbfgs.py holds
+// the same logic as host code (used for line_search_fn=None and as the CPU-tested restatement of torch's functions);
+// tests/test_gpu_optim.py holds both to torch's iteration / evaluation counts.
 #include <cooperative_groups.h>
 #include <math.h>
 
@@ -46,6 +63,11 @@ struct LbState {
   double br[2], br_f[2], br_gtd[2];
   int br_n, low, high, done, insuf, ls_iter, max_ls, ls_evals;
   int status;
+  // hand-over between the kernels of one advance
+  int begin;        // a new outer iteration starts: kernels 2-3 run
+  int trial;        // kernel 4 writes the first trial point of a new line search
+  int slot_new;     // ring slot of the candidate pair (or -1)
+  double trial_t;
 };
 
 struct LbStatus {   // copied to the host after every advance
@@ -54,7 +76,13 @@ struct LbStatus {   // copied to the host after every advance
 };
 
 struct LbVectors {  // all [P] unless noted; carved from the workspace
-  float *d, *prev_g, *x0, *gp, *b0, *b1, *S, *Y, *rho, *h_diag;   // S, Y: [(hist+1), P]; rho: [hist+1]; h_diag: [1]
+  float *d, *prev_g, *x0, *gp, *b0, *b1, *S, *Y;   // S, Y: [(hist+1), P] ring of curvature pairs
+  double *SS, *SY, *YY;     // Gram matrices over ring slots, [cap][cap]: s_p.s_q, s_p.y_q, y_p.y_q
+  double *delta;            // [2 cap + 2]: coefficients of d over {s_p}, {y_p}, g; last entry: H_diag
+  double *dots_partial;     // [grid][2 cap][3]: per-CTA partial dots of every stored vector with s_new, y_new, g
+  double *stats_partial;    // [grid][4]: per-CTA partial g.d, |g|_1, max|d|
+  unsigned* counters;       // [2] arrival counters of the "last CTA finishes the job" reductions
+  int grid;                 // CTAs of the whole-chip kernels
 };
 
 // ---- cluster-wide deterministic reductions: every thread of every CTA gets the same value ----
@@ -62,7 +90,6 @@ struct LbShared {
   float warp_buf[32];
   float slot[2][8];     // per-call partials of this CTA (up to 8 quantities), double-buffered
   float bcast[8];
-  float al[kLbMaxHistory];
   // decisions of thread 0 broadcast to the CTA
   int copy_src[4], copy_dst[4], n_copy;
   int do_finish, do_begin, do_trial, status;
@@ -129,74 +156,6 @@ __device__ __forceinline__ void lb_stats(cg::cluster_group& cl, LbShared& sh, co
   phase ^= 1;
 }
 
-__device__ __forceinline__ float lb_dot_sum(cg::cluster_group& cl, LbShared& sh, float part, int& phase) {
-  part = lb_block_sum(part, sh.warp_buf);
-  __syncthreads();
-  if (threadIdx.x == 0) sh.slot[phase][0] = part;
-  cl.sync();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (unsigned r = 0; r < cl.num_blocks(); ++r) t += *cl.map_shared_rank(&sh.slot[phase][0], r);
-    sh.bcast[0] = t;
-  }
-  __syncthreads();
-  phase ^= 1;
-  return sh.bcast[0];
-}
-
-// d = -H g by the two-loop recursion (torch/optim/lbfgs.py:432-447); slot(i) = (head + i) % cap, i = 0 oldest
-__device__ void lb_two_loop(cg::cluster_group& cl, LbShared& sh, const LbVectors& V, const float* g, int cap, int m, int head,
-                            long long P, long long lo, long long hi, int& phase) {
-  float* d = V.d;
-  const float* s_last = m > 0 ? V.S + (long long)((head + m - 1) % cap) * P : nullptr;
-  float part = 0.f;
-  for (long long i = lo + threadIdx.x; i < hi; i += kLbThreads) {
-    const float q = -g[i];
-    d[i] = q;
-    if (s_last) part = fmaf(s_last[i], q, part);
-  }
-  if (m > 0) {
-    float a_i = lb_dot_sum(cl, sh, part, phase) * V.rho[(head + m - 1) % cap];
-    if (threadIdx.x == 0) sh.al[m - 1] = a_i;
-    for (int i = m - 1; i >= 0; --i) {
-      const float* y = V.Y + (long long)((head + i) % cap) * P;
-      const float* sn = i > 0 ? V.S + (long long)((head + i - 1) % cap) * P : nullptr;
-      float p2 = 0.f;
-      for (long long e = lo + threadIdx.x; e < hi; e += kLbThreads) {
-        const float q = fmaf(-a_i, y[e], d[e]);
-        d[e] = q;
-        if (sn) p2 = fmaf(sn[e], q, p2);
-      }
-      if (i > 0) {
-        a_i = lb_dot_sum(cl, sh, p2, phase) * V.rho[(head + i - 1) % cap];
-        if (threadIdx.x == 0) sh.al[i - 1] = a_i;
-      }
-    }
-  }
-  const float hd = *V.h_diag;
-  const float* y0 = m > 0 ? V.Y + (long long)(head % cap) * P : nullptr;
-  part = 0.f;
-  for (long long e = lo + threadIdx.x; e < hi; e += kLbThreads) {
-    const float r = d[e] * hd;
-    d[e] = r;
-    if (y0) part = fmaf(y0[e], r, part);
-  }
-  for (int i = 0; i < m; ++i) {
-    const int sl = (head + i) % cap;
-    const float be = lb_dot_sum(cl, sh, part, phase) * V.rho[sl];
-    __syncthreads();
-    const float coef = sh.al[i] - be;
-    const float* s = V.S + (long long)sl * P;
-    const float* yn = i + 1 < m ? V.Y + (long long)((head + i + 1) % cap) * P : nullptr;
-    part = 0.f;
-    for (long long e = lo + threadIdx.x; e < hi; e += kLbThreads) {
-      const float r = fmaf(coef, s[e], d[e]);
-      d[e] = r;
-      if (yn) part = fmaf(yn[e], r, part);
-    }
-  }
-}
-
 // torch/optim/lbfgs.py:12-37 (IEEE division: a collapsed bracket yields inf / nan and falls through like torch's tensors)
 __device__ double lb_cubic(double x1, double f1, double g1, double x2, double f2, double g2, bool has_bounds, double bmin,
                            double bmax) {
@@ -221,6 +180,14 @@ __device__ double lb_cubic(double x1, double f1, double g1, double x2, double f2
 
 enum { LB_BUF_G = 0, LB_BUF_GP = 1, LB_BUF_B0 = 2, LB_BUF_B1 = 3, LB_BUF_PREVG = 4 };
 
+__device__ __forceinline__ void lb_write_status(const LbState& st, LbStatus* out) {
+  LbStatus o;
+  o.code = st.status, o.n_iter = st.n_iter, o.current_evals = st.current_evals, o.n_iter_total = st.n_iter_total;
+  o.func_evals_total = st.func_evals_total, o.ph = st.ph, o.used = st.used, o.pad = 0;
+  o.t = st.t, o.loss = st.loss, o.first_loss = st.first_loss, o.gtd = st.gtd, o.d_norm = st.d_norm;
+  *out = o;
+}
+
 // One transition of the optimiser between two closure evaluations.  `g` holds the gradient and *loss_dev the loss at
 // `flat`; on return either `flat` is the next trial point (status EVAL) or the step() call is over (status DONE).
 __global__ void __cluster_dims__(kLbCtas, 1, 1) __launch_bounds__(kLbThreads)
@@ -233,7 +200,10 @@ __global__ void __cluster_dims__(kLbCtas, 1, 1) __launch_bounds__(kLbThreads)
   const long long lo = per * cl.block_rank();
   const long long hi = lo + per < P ? lo + per : P;
   int phase = 0;
-  if (threadIdx.x == 0) st = *st_g;
+  if (threadIdx.x == 0) {
+    st = *st_g;
+    st.begin = 0, st.trial = 0, st.slot_new = -1;
+  }
   __syncthreads();
   const int cap = st.hist + 1;
   float* bufs[5] = {g, V.gp, V.b0, V.b1, V.prev_g};
@@ -399,88 +369,18 @@ __global__ void __cluster_dims__(kLbCtas, 1, 1) __launch_bounds__(kLbThreads)
     __syncthreads();
   }
 
-  if (sh.do_begin) {
-    // ---- start of an outer iteration (lbfgs.py:394-487) ----
-    if (threadIdx.x == 0) {
-      st.n_iter += 1;
-      st.n_iter_total += 1;
-    }
-    __syncthreads();
-    if (st.n_iter_total == 1) {
-      if (threadIdx.x == 0) st.used = 0, st.head = 0;
-      if (cl.block_rank() == 0 && threadIdx.x == 0) *V.h_diag = 1.f;
-    } else {
-      // curvature pair into the free ring slot: y = g - prev_g, s = t d; kept only if y.s > 1e-10
-      const int slot = (st.head + st.used) % cap;
-      float* Ys = V.Y + (long long)slot * P;
-      float* Ss = V.S + (long long)slot * P;
-      const float tf = (float)st.t;
-      for (long long i = lo + threadIdx.x; i < hi; i += kLbThreads) {
-        Ys[i] = g[i] - V.prev_g[i];
-        Ss[i] = V.d[i] * tf;
-      }
-      __syncthreads();
-      lb_stats(cl, sh, Ys, Ss, lo, hi, phase);
-      const double ys = (double)sh.bcast[0], yy = (double)sh.bcast[4];
-      if (ys > 1e-10) {
-        if (threadIdx.x == 0) {
-          if (st.used == st.hist) st.head = (st.head + 1) % cap;
-          else st.used += 1;
-        }
-        if (cl.block_rank() == 0 && threadIdx.x == 0) {
-          V.rho[slot] = (float)(1.0 / ys);
-          *V.h_diag = (float)(ys / yy);
-        }
-      }
-    }
-    __threadfence();
-    cl.sync();      // rho / h_diag written by rank 0 are visible to every CTA; st.used / st.head settled
-    lb_two_loop(cl, sh, V, g, cap, st.used, st.head, P, lo, hi, phase);
-    __syncthreads();
-    for (long long i = lo + threadIdx.x; i < hi; i += kLbThreads) V.prev_g[i] = g[i];
-    cl.sync();      // d complete everywhere before the statistics
-    lb_stats(cl, sh, g, V.d, lo, hi, phase);
-    if (threadIdx.x == 0) {
-      st.prev_loss = st.loss;
-      st.gtd = (double)sh.bcast[0];
-      st.d_norm = (double)sh.bcast[3];
-      const double g_l1 = (double)sh.bcast[1];
-      double t;
-      if (st.n_iter_total == 1) {
-        const double inv = 1.0 / g_l1;
-        t = (inv < 1.0 ? inv : 1.0) * st.lr;      // min(1., 1. / |g|_1) * lr
-      } else {
-        t = st.lr;
-      }
-      st.t = t;
-      if (st.gtd > -st.tol_change) {              // lbfgs.py:463
-        sh.status = LB_STATUS_DONE;
-      } else {
-        // line search set-up (lbfgs.py:40-56 with max_ls = max_eval - current_evals, :486)
-        st.f0 = st.loss, st.gtd0 = st.gtd, st.ls_t = t;
-        st.t_prev = 0.0, st.f_prev = st.loss, st.gtd_prev = st.gtd;
-        st.br_n = 0, st.done = 0, st.insuf = 0, st.ls_iter = 0, st.ls_evals = 0;
-        st.max_ls = st.max_eval - st.current_evals;
-        st.low = 0, st.high = 1;
-        st.ph = LB_PH_BRACKET;
-        sh.do_trial = 2, sh.trial_t = t;
-      }
-    }
-    __syncthreads();
+  if (sh.do_begin && threadIdx.x == 0) {
+    // a new outer iteration starts (lbfgs.py:394-402): kernels 2-4 of this advance do the work
+    st.n_iter += 1;
+    st.n_iter_total += 1;
+    st.begin = 1;
+    st.slot_new = st.n_iter_total > 1 ? (st.head + st.used) % cap : -1;
   }
+  __syncthreads();
 
-  if (sh.do_trial) {
+  if (sh.do_trial) {   // next trial point of the running line search
     const float tt = (float)sh.trial_t;
-    if (sh.do_trial == 2) {   // first trial of a line search: x0 = x, g_prev = g (torch clones both)
-      for (long long i = lo + threadIdx.x; i < hi; i += kLbThreads) {
-        const float x = flat[i];
-        V.x0[i] = x;
-        V.gp[i] = g[i];
-        flat[i] = fmaf(tt, V.d[i], x);
-      }
-    } else {
-      for (long long i = lo + threadIdx.x; i < hi; i += kLbThreads) flat[i] = fmaf(tt, V.d[i], V.x0[i]);
-    }
+    for (long long i = lo + threadIdx.x; i < hi; i += kLbThreads) flat[i] = fmaf(tt, V.d[i], V.x0[i]);
     if (threadIdx.x == 0) sh.status = LB_STATUS_EVAL;
   }
   __syncthreads();
@@ -489,35 +389,318 @@ __global__ void __cluster_dims__(kLbCtas, 1, 1) __launch_bounds__(kLbThreads)
     st.status = sh.status;
     if (sh.status == LB_STATUS_DONE) st.ph = LB_PH_DONE;
     *st_g = st;
-    LbStatus o;
-    o.code = sh.status, o.n_iter = st.n_iter, o.current_evals = st.current_evals, o.n_iter_total = st.n_iter_total;
-    o.func_evals_total = st.func_evals_total, o.ph = st.ph, o.used = st.used, o.pad = 0;
-    o.t = st.t, o.loss = st.loss, o.first_loss = st.first_loss, o.gtd = st.gtd, o.d_norm = st.d_norm;
-    *status_out = o;
+    lb_write_status(st, status_out);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Kernel 2: candidate pair + every dot product the iteration needs in one pass; last CTA: Gram update + coefficient two-loop
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kVlThreads = 256;
+
+__device__ __forceinline__ double vl_warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// sum over the CTA, result to every thread (fixed order)
+__device__ __forceinline__ double vl_block_sum(double v, double* warp_buf) {
+  v = vl_warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) warp_buf[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < kVlThreads / 32; ++i) t += warp_buf[i];
+  return t;
+}
+__device__ __forceinline__ bool vl_slot_active(int p, int head, int used, int cap, int slot_new) {
+  const int rel = (p - head + cap) % cap;
+  return rel < used || p == slot_new;
+}
+// true in every thread of exactly one CTA: the last one to arrive (its view of the other CTAs' global writes is complete)
+__device__ __forceinline__ bool vl_last_cta(unsigned* counter) {
+  __shared__ unsigned ticket;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) ticket = atomicAdd(counter, 1u);
+  __syncthreads();
+  const bool last = ticket == gridDim.x - 1;
+  if (last) {
+    __threadfence();
+    if (threadIdx.x == 0) *counter = 0;   // re-armed for the next launch
+  }
+  return last;
+}
+
+__global__ void __launch_bounds__(kVlThreads)
+    vl_dots_kernel(LbState* __restrict__ st_g, LbVectors V, const float* __restrict__ g, long long P) {
+  if (!st_g->begin) return;
+  __shared__ double warp_buf[kVlThreads / 32];
+  __shared__ double al[kLbMaxHistory + 1];
+  const int cap = st_g->hist + 1;
+  const int head = st_g->head, used = st_g->used, slot_new = st_g->slot_new;
+  const long long per = ((P + gridDim.x - 1) / gridDim.x + 3) & ~3LL;
+  const long long lo = per * blockIdx.x;
+  const long long hi = lo + per < P ? lo + per : P;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // candidate pair into the free ring slot: y = g - prev_g, s = t d (lbfgs.py:404-406)
+  if (slot_new >= 0) {
+    float* Ys = V.Y + (long long)slot_new * P;
+    float* Ss = V.S + (long long)slot_new * P;
+    const float tf = (float)st_g->t;
+    for (long long i = lo + threadIdx.x; i < hi; i += kVlThreads) {
+      Ys[i] = g[i] - V.prev_g[i];
+      Ss[i] = V.d[i] * tf;
+    }
+  }
+  __syncthreads();
+  const float* s_new = slot_new >= 0 ? V.S + (long long)slot_new * P : nullptr;
+  const float* y_new = slot_new >= 0 ? V.Y + (long long)slot_new * P : nullptr;
+  double* part = V.dots_partial + (size_t)blockIdx.x * (2 * cap) * 3;
+  for (int v = warp; v < 2 * cap; v += kVlThreads / 32) {
+    const int pslot = v < cap ? v : v - cap;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    if (vl_slot_active(pslot, head, used, cap, slot_new)) {
+      const float* vec = (v < cap ? V.S : V.Y) + (long long)pslot * P;
+      for (long long i = lo + lane; i < hi; i += 32) {
+        const double x = (double)vec[i];
+        if (s_new) a0 = fma(x, (double)s_new[i], a0), a1 = fma(x, (double)y_new[i], a1);
+        a2 = fma(x, (double)g[i], a2);
+      }
+      a0 = vl_warp_sum(a0), a1 = vl_warp_sum(a1), a2 = vl_warp_sum(a2);
+    }
+    if (lane == 0) part[v * 3] = a0, part[v * 3 + 1] = a1, part[v * 3 + 2] = a2;
+  }
+  if (!vl_last_cta(V.counters)) return;
+
+  // ---------------- last CTA: reduce, accept the pair, update the Gram matrices, coefficient two-loop ----------------
+  double* dS = V.delta;            // [cap] coefficient of s_p
+  double* dY = V.delta + cap;      // [cap] coefficient of y_p
+  __shared__ double dot_g_s[kLbMaxHistory + 1], dot_g_y[kLbMaxHistory + 1];
+  __shared__ int sh_head, sh_used;
+  // per stored vector: its dots with s_new, y_new, g (fixed summation order over the CTAs)
+  for (int v = threadIdx.x; v < 2 * cap; v += kVlThreads) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (unsigned c = 0; c < gridDim.x; ++c) {
+      const double* pc = V.dots_partial + ((size_t)c * (2 * cap) + v) * 3;
+      a0 += pc[0], a1 += pc[1], a2 += pc[2];
+    }
+    const int pslot = v < cap ? v : v - cap;
+    if (v < cap) dot_g_s[pslot] = a2; else dot_g_y[pslot] = a2;
+    if (slot_new >= 0) {
+      // Gram rows / columns of the candidate slot (used only once the pair is accepted; harmless otherwise because a
+      // rejected candidate's slot is rewritten before it can ever become active)
+      if (v < cap) {
+        V.SS[(size_t)slot_new * cap + pslot] = a0, V.SS[(size_t)pslot * cap + slot_new] = a0;   // s_new . s_p
+        if (pslot != slot_new) V.SY[(size_t)pslot * cap + slot_new] = a1;                        // s_p . y_new (the diagonal
+                                                                                                  // comes from the y row below)
+      } else {
+        V.SY[(size_t)slot_new * cap + pslot] = a0;                                                // s_new . y_p
+        V.YY[(size_t)slot_new * cap + pslot] = a1, V.YY[(size_t)pslot * cap + slot_new] = a1;   // y_new . y_p
+      }
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int h = head, u = used;
+    double hd = V.delta[2 * cap + 1];
+    if (st_g->n_iter_total == 1) {
+      h = 0, u = 0, hd = 1.0;                                   // lbfgs.py:396-402
+    } else if (slot_new >= 0) {
+      const double ys = V.SY[(size_t)slot_new * cap + slot_new], yy = V.YY[(size_t)slot_new * cap + slot_new];
+      if (ys > 1e-10) {                                          // lbfgs.py:408-421
+        if (u == st_g->hist) h = (h + 1) % cap;
+        else u += 1;
+        hd = ys / yy;
+      }
+    }
+    V.delta[2 * cap + 1] = hd;
+    sh_head = h, sh_used = u;
+    st_g->head = h, st_g->used = u;
+  }
+  __syncthreads();
+  const int h2 = sh_head, m = sh_used;
+  const double hdiag = V.delta[2 * cap + 1];
+  // two-loop recursion on coefficients (lbfgs.py:432-447): q = -g; logical pair i sits in slot (h2 + i) % cap
+  for (int p_ = threadIdx.x; p_ < cap; p_ += kVlThreads) dS[p_] = 0.0, dY[p_] = 0.0;
+  __shared__ double dG;
+  if (threadIdx.x == 0) dG = -1.0;
+  __syncthreads();
+  for (int i = m - 1; i >= 0; --i) {
+    const int pi = (h2 + i) % cap;
+    // s_i . q = sum_j dS_j (s_i.s_j) + dY_j (s_i.y_j) + dG (s_i.g)
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < m; j += kVlThreads) {
+      const int pj = (h2 + j) % cap;
+      acc = fma(dS[pj], V.SS[(size_t)pi * cap + pj], acc);
+      acc = fma(dY[pj], V.SY[(size_t)pi * cap + pj], acc);
+    }
+    const double sq = vl_block_sum(acc, warp_buf) + dG * dot_g_s[pi];
+    const double a_i = sq / V.SY[(size_t)pi * cap + pi];         // ro_i = 1 / (y_i . s_i)
+    __syncthreads();
+    if (threadIdx.x == 0) al[i] = a_i, dY[pi] -= a_i;
+    __syncthreads();
+  }
+  for (int p_ = threadIdx.x; p_ < cap; p_ += kVlThreads) dS[p_] *= hdiag, dY[p_] *= hdiag;
+  if (threadIdx.x == 0) dG *= hdiag;
+  __syncthreads();
+  for (int i = 0; i < m; ++i) {
+    const int pi = (h2 + i) % cap;
+    // y_i . r = sum_j dS_j (s_j.y_i) + dY_j (y_i.y_j) + dG (y_i.g)
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < m; j += kVlThreads) {
+      const int pj = (h2 + j) % cap;
+      acc = fma(dS[pj], V.SY[(size_t)pj * cap + pi], acc);
+      acc = fma(dY[pj], V.YY[(size_t)pi * cap + pj], acc);
+    }
+    const double yr = vl_block_sum(acc, warp_buf) + dG * dot_g_y[pi];
+    const double be = yr / V.SY[(size_t)pi * cap + pi];
+    __syncthreads();
+    if (threadIdx.x == 0) dS[pi] += al[i] - be;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) V.delta[2 * cap] = dG;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Kernel 3: d = sum_j delta_j b_j (second pass over the history), prev_g = g, statistics; last CTA: step length, line-search set-up
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kVlThreads)
+    vl_combine_kernel(LbState* __restrict__ st_g, LbVectors V, const float* __restrict__ g, LbStatus* __restrict__ status_out,
+                      long long P) {
+  if (!st_g->begin) return;
+  __shared__ double cS[kLbMaxHistory + 1], cY[kLbMaxHistory + 1];
+  __shared__ double warp_buf[kVlThreads / 32];
+  __shared__ float fmax_buf[kVlThreads / 32];
+  const int cap = st_g->hist + 1;
+  const int head = st_g->head, m = st_g->used;
+  for (int p_ = threadIdx.x; p_ < cap; p_ += kVlThreads) cS[p_] = V.delta[p_], cY[p_] = V.delta[cap + p_];
+  __syncthreads();
+  const double cG = V.delta[2 * cap];
+  double gd = 0.0, l1 = 0.0;
+  float md = 0.f;
+  for (long long i = (long long)blockIdx.x * kVlThreads + threadIdx.x; i < P; i += (long long)gridDim.x * kVlThreads) {
+    const float gi = g[i];
+    double acc = cG * (double)gi;
+    for (int j = 0; j < m; ++j) {
+      const int pj = (head + j) % cap;
+      acc = fma(cS[pj], (double)V.S[(long long)pj * P + i], acc);
+      acc = fma(cY[pj], (double)V.Y[(long long)pj * P + i], acc);
+    }
+    const float di = (float)acc;
+    V.d[i] = di;
+    V.prev_g[i] = gi;                                           // prev_flat_grad.copy_(flat_grad), lbfgs.py:449-452
+    gd = fma((double)gi, (double)di, gd);
+    l1 += (double)fabsf(gi);
+    md = lb_nan_max(md, fabsf(di));
+  }
+  gd = vl_block_sum(gd, warp_buf);
+  l1 = vl_block_sum(l1, warp_buf);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) md = lb_nan_max(md, __shfl_xor_sync(0xffffffffu, md, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) fmax_buf[threadIdx.x >> 5] = md;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mm = 0.f;
+    for (int i = 0; i < kVlThreads / 32; ++i) mm = lb_nan_max(mm, fmax_buf[i]);
+    double* sp = V.stats_partial + (size_t)blockIdx.x * 4;
+    sp[0] = gd, sp[1] = l1, sp[2] = (double)mm;
+  }
+  if (!vl_last_cta(V.counters + 1)) return;
+  if (threadIdx.x != 0) return;
+  // ---------------- last CTA, one thread: lbfgs.py:449-487 ----------------
+  double gtd = 0.0, g_l1 = 0.0;
+  float dmax = 0.f;
+  for (unsigned c = 0; c < gridDim.x; ++c) {
+    const double* sp = V.stats_partial + (size_t)c * 4;
+    gtd += sp[0], g_l1 += sp[1];
+    dmax = lb_nan_max(dmax, (float)sp[2]);
+  }
+  LbState st = *st_g;
+  st.prev_loss = st.loss;
+  st.gtd = gtd;
+  st.d_norm = (double)dmax;
+  double t;
+  if (st.n_iter_total == 1) {
+    const double inv = 1.0 / g_l1;
+    t = (inv < 1.0 ? inv : 1.0) * st.lr;          // min(1., 1. / |g|_1) * lr
+  } else {
+    t = st.lr;
+  }
+  st.t = t;
+  if (st.gtd > -st.tol_change) {                  // lbfgs.py:463
+    st.status = LB_STATUS_DONE;
+    st.ph = LB_PH_DONE;
+  } else {
+    // line search set-up (lbfgs.py:40-56 with max_ls = max_eval - current_evals, :486)
+    st.f0 = st.loss, st.gtd0 = st.gtd, st.ls_t = t;
+    st.t_prev = 0.0, st.f_prev = st.loss, st.gtd_prev = st.gtd;
+    st.br_n = 0, st.done = 0, st.insuf = 0, st.ls_iter = 0, st.ls_evals = 0;
+    st.max_ls = st.max_eval - st.current_evals;
+    st.low = 0, st.high = 1;
+    st.ph = LB_PH_BRACKET;
+    st.trial = 1, st.trial_t = t;
+    st.status = LB_STATUS_EVAL;
+  }
+  *st_g = st;
+  lb_write_status(st, status_out);
+}
+
+// Kernel 4: first trial point of a new line search: x0 = x, g_prev = g (torch clones both), x = x0 + t d
+__global__ void __launch_bounds__(kVlThreads)
+    lbfgs_trial_kernel(const LbState* __restrict__ st_g, LbVectors V, float* __restrict__ flat, const float* __restrict__ g, long long P) {
+  if (!st_g->begin || !st_g->trial) return;
+  const float tt = (float)st_g->trial_t;
+  for (long long i = (long long)blockIdx.x * kVlThreads + threadIdx.x; i < P; i += (long long)gridDim.x * kVlThreads) {
+    const float x = flat[i];
+    V.x0[i] = x;
+    V.gp[i] = g[i];
+    flat[i] = fmaf(tt, V.d[i], x);
   }
 }
 
 static size_t lb_align(size_t x) { return (x + 255) & ~size_t(255); }
 
+constexpr int kVlMaxGrid = 592;   // 148 SMs x 4: the whole-chip kernels never launch more CTAs than this
+
 struct LbLayout {
-  size_t state, status, vec, hist, rho, total;
+  size_t state, status, counters, vec, hist, gram, delta, dots, stats, total;
 };
 static LbLayout lb_layout(long long P, int hist) {
+  const size_t cap = (size_t)hist + 1;
   LbLayout L;
   L.state = 0;
   L.status = lb_align(sizeof(LbState));
-  size_t o = L.status + lb_align(sizeof(LbStatus));
-  L.vec = o;
+  L.counters = L.status + lb_align(sizeof(LbStatus));
+  size_t o = L.counters + 256;
+  L.gram = o;
+  o += 3 * lb_align(cap * cap * 8);
+  L.delta = o;
+  o += lb_align((2 * cap + 2) * 8);
+  L.dots = o;
+  o += lb_align((size_t)kVlMaxGrid * 2 * cap * 3 * 8);
+  L.stats = o;
+  o += lb_align((size_t)kVlMaxGrid * 4 * 8);
+  L.vec = o;                       // everything before this offset is zeroed by a reset
   o += 6 * lb_align((size_t)P * 4);
   L.hist = o;
-  o += 2 * lb_align((size_t)(hist + 1) * (size_t)P * 4);
-  L.rho = o;
-  o += lb_align((size_t)(hist + 2) * 4);
+  o += 2 * lb_align(cap * (size_t)P * 4);
   L.total = o;
   return L;
 }
+static int vl_grid(long long P) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long g = (P + 1023) / 1024;           // at least 1024 elements per CTA
+  const long long cap_g = (long long)sms * 4 < kVlMaxGrid ? (long long)sms * 4 : kVlMaxGrid;
+  if (g > cap_g) g = cap_g;
+  return (int)(g < 1 ? 1 : g);
+}
 static LbVectors lb_vectors(void* ws, long long P, int hist) {
   const LbLayout L = lb_layout(P, hist);
+  const size_t cap = (size_t)hist + 1;
   char* b = reinterpret_cast<char*>(ws);
   const size_t vs = lb_align((size_t)P * 4);
   LbVectors V;
@@ -528,9 +711,15 @@ static LbVectors lb_vectors(void* ws, long long P, int hist) {
   V.b0 = reinterpret_cast<float*>(b + L.vec + 4 * vs);
   V.b1 = reinterpret_cast<float*>(b + L.vec + 5 * vs);
   V.S = reinterpret_cast<float*>(b + L.hist);
-  V.Y = reinterpret_cast<float*>(b + L.hist + lb_align((size_t)(hist + 1) * (size_t)P * 4));
-  V.rho = reinterpret_cast<float*>(b + L.rho);
-  V.h_diag = V.rho + hist + 1;
+  V.Y = reinterpret_cast<float*>(b + L.hist + lb_align(cap * (size_t)P * 4));
+  V.SS = reinterpret_cast<double*>(b + L.gram);
+  V.SY = reinterpret_cast<double*>(b + L.gram + lb_align(cap * cap * 8));
+  V.YY = reinterpret_cast<double*>(b + L.gram + 2 * lb_align(cap * cap * 8));
+  V.delta = reinterpret_cast<double*>(b + L.delta);
+  V.dots_partial = reinterpret_cast<double*>(b + L.dots);
+  V.stats_partial = reinterpret_cast<double*>(b + L.stats);
+  V.counters = reinterpret_cast<unsigned*>(b + L.counters);
+  V.grid = vl_grid(P);
   return V;
 }
 
@@ -546,6 +735,14 @@ __global__ void lbfgs_begin_kernel(LbState* st, double lr, double tol_grad, doub
   s.max_iter = max_iter, s.max_eval = max_eval, s.hist = hist;
   s.ph = LB_PH_START, s.n_iter = 0, s.current_evals = 0, s.status = 0;
   *st = s;
+}
+
+// bench hook: pretend the history is full and an iteration begins (the vectors hold whatever the caller put there)
+__global__ void lbfgs_probe_setup_kernel(LbState* st, int hist) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  st->hist = hist, st->head = 0, st->used = hist - 1, st->slot_new = hist - 1;
+  st->n_iter_total = 5, st->begin = 1, st->trial = 0, st->t = 1.0, st->lr = 1.0, st->tol_change = 0.0;
+  st->max_eval = 100, st->current_evals = 1, st->loss = 1.0;
 }
 
 }  // namespace pinn
@@ -578,10 +775,36 @@ extern "C" int pinn_lbfgs_advance(void* workspace, int64_t n_params, int32_t his
   cudaStream_t st = (cudaStream_t)stream;
   const LbLayout L = lb_layout(n_params, history_size);
   char* b = reinterpret_cast<char*>(workspace);
+  LbState* state = reinterpret_cast<LbState*>(b);
   LbStatus* dev_status = reinterpret_cast<LbStatus*>(b + L.status);
-  lbfgs_advance_kernel<<<kLbCtas, kLbThreads, 0, st>>>(reinterpret_cast<LbState*>(b), lb_vectors(workspace, n_params, history_size),
-                                                       flat_params, grad, loss, dev_status, (long long)n_params);
+  const LbVectors V = lb_vectors(workspace, n_params, history_size);
+  const long long P = (long long)n_params;
+  lbfgs_advance_kernel<<<kLbCtas, kLbThreads, 0, st>>>(state, V, flat_params, grad, loss, dev_status, P);
+  // the next three return at once unless the kernel above started a new outer iteration (decided on the device)
+  vl_dots_kernel<<<V.grid, kVlThreads, 0, st>>>(state, V, grad, P);
+  vl_combine_kernel<<<V.grid, kVlThreads, 0, st>>>(state, V, grad, dev_status, P);
+  lbfgs_trial_kernel<<<V.grid, kVlThreads, 0, st>>>(state, V, flat_params, grad, P);
   PINN_CUDA(cudaGetLastError());
   PINN_CUDA(cudaMemcpyAsync(status_host, dev_status, sizeof(LbStatus), cudaMemcpyDeviceToHost, st));
+  return PINN_OK;
+}
+
+// Standalone timing hook for bench.py ("L-BFGS direction ... HBM-bound, reported as GB/s"): runs kernels 2-3
+// (the two passes over the history) on a workspace whose history is full, without touching the optimiser's state machine.
+extern "C" int pinn_lbfgs_direction_probe(void* workspace, int64_t n_params, int32_t history_size, const float* grad,
+                                          double* bytes_out, void* stream) {
+  if (!workspace || !grad || n_params <= 0) return set_error("lbfgs_direction_probe: bad arguments"), PINN_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const LbLayout L = lb_layout(n_params, history_size);
+  char* b = reinterpret_cast<char*>(workspace);
+  LbState* state = reinterpret_cast<LbState*>(b);
+  const LbVectors V = lb_vectors(workspace, n_params, history_size);
+  lbfgs_probe_setup_kernel<<<1, 32, 0, st>>>(state, history_size);
+  vl_dots_kernel<<<V.grid, kVlThreads, 0, st>>>(state, V, grad, (long long)n_params);
+  vl_combine_kernel<<<V.grid, kVlThreads, 0, st>>>(state, V, grad, reinterpret_cast<LbStatus*>(b + L.status), (long long)n_params);
+  PINN_CUDA(cudaGetLastError());
+  // algorithmic bytes: both passes read the 2 m P history once; pass 1 also reads g, prev_g, d and writes the new pair,
+  // pass 2 reads g and writes d, prev_g
+  if (bytes_out) *bytes_out = 4.0 * (double)n_params * (2.0 * 2.0 * history_size + 5.0 + 3.0);
   return PINN_OK;
 }
