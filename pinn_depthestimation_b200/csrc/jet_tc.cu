@@ -89,7 +89,7 @@ constexpr int TC_EDGE_E2 = TC_EDGE_E1 + 4 * TC_STAGE_FLOATS;
 constexpr int TC_EDGE_FLOATS = TC_EDGE_E2 + 4 * 1024;
 constexpr int TC_GIMG = 2 * TC_IMG;        // floats per weight-gradient operand image (Zbar_l and a_{l-1} interleaved)
 constexpr int TC_WCHUNKS = TC_H * (TC_H / 2) * 4 / TC_STAGE_BYTES;   // 8 chunks per half-width weight image
-constexpr int TC_MAX_HH = 7;               // hidden->hidden layers whose bias gradients are staged in shared memory
+constexpr int TC_MAX_HH = 7;               // hidden->hidden layers whose bias gradients are staged in shared memory (deeper ones: global atomics)
 
 struct TcArgs {
   const float* params;
@@ -1052,7 +1052,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       // ---- Abar_{L-2} = seeds * W_last (tensor core), through the activation of layer L-2 -> Zbar_{L-2} in place ----
       {
         float* zdst = slab + (size_t)(L - 3) * TC_GIMG;
-        float* dbl = db_s + (size_t)(L - 3) * TC_H;
+        // bias gradients of the first TC_MAX_HH hidden->hidden layers are staged in shared memory and flushed once at kernel
+        // exit; deeper nets add the rest straight into the flat gradient (one atomic per feature per tile)
+        float* dbl = (L - 3 < TC_MAX_HH) ? db_s + (size_t)(L - 3) * TC_H
+                                         : A.grad + P0 + (long long)(L - 3) * PH + (long long)TC_H * TC_H;
         wait_mma();
 #pragma unroll
         for (int b = 0; b < TC_NBLK; ++b) {
@@ -1065,10 +1068,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           st_op_block(b, ab);
           signal_slice();                   // (the adjoint job of layer L-2 starts once all four slices are in)
           st_img_block(zdst, b, ab);
-          if (L - 3 < TC_MAX_HH) {
-            if (X3) db_block_x3(dbl, b, zb0);
-            else db_block(dbl, b, ab[0]);
-          }
+          if (X3) db_block_x3(dbl, b, zb0);
+          else db_block(dbl, b, ab[0]);
         }
       }
       publish_spill(&zt_ready[nzs++ & 1]);
@@ -1114,7 +1115,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         {
           const float* aimg = slab + (size_t)(l - 1) * TC_GIMG + IMG_A;
           float* zdst = slab + (size_t)(l >= 2 ? l - 2 : 0) * TC_GIMG;
-          float* dbl = db_s + (size_t)(l >= 2 ? l - 2 : 0) * TC_H;
+          const int hh = l >= 2 ? l - 2 : 0;
+          float* dbl = (hh < TC_MAX_HH) ? db_s + (size_t)hh * TC_H
+                                        : A.grad + P0 + (long long)hh * PH + (long long)TC_H * TC_H;
           const bool hidden = l > 1;
           float act[TC_NBLK][4][4];
 #pragma unroll
@@ -1132,10 +1135,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             if (hidden) {
               signal_slice();               // (the adjoint job of layer l-1 starts once all four slices are in)
               st_img_block(zdst, b, ab);
-              if (l - 2 < TC_MAX_HH) {
-                if (X3) db_block_x3(dbl, b, zb0);
-                else db_block(dbl, b, ab[0]);
-              }
+              if (X3) db_block_x3(dbl, b, zb0);
+              else db_block(dbl, b, ab[0]);
             }
           }
         }
@@ -1299,7 +1300,6 @@ bool tc_supported(const pinn_desc_t* D, const char** why) {
   const int L = D->n_linear;
   *why = "";
   if (L < 3) return *why = "needs at least two hidden layers", false;
-  if (L - 2 > TC_MAX_HH) return *why = "at most 8 hidden layers (bias gradients of 7 hidden->hidden layers are staged in shared memory)", false;
   for (int i = 1; i < L; ++i)
     if (D->widths[i] != TC_H) return *why = "every hidden layer must be 256 wide", false;
   if (D->activation != PINN_ACT_TANH) return *why = "tanh activation only", false;

@@ -105,14 +105,36 @@ def test_tf32_is_refused_for_nets_it_does_not_cover():
         JetLoss(spec, torch.zeros(8, 2, device=dev), torch.zeros(8, 2, device=dev))
 
 
-def test_tf32_is_refused_for_nets_deeper_than_the_bias_gradient_staging():
+@pytest.mark.parametrize("prec,lt,gt", [("tf32", TF32_LOSS_RTOL, TF32_GRAD_RTOL), ("tf32x3", 3e-6, 3e-5)])
+def test_tensor_core_path_on_a_net_deeper_than_the_bias_gradient_staging(prec, lt, gt):
+    """11 hidden layers: the bias gradients of hidden->hidden layers 8.. go straight into the flat gradient."""
     from pinn_depthestimation_b200 import PassSpec
     from pinn_depthestimation_b200.fused import JetLoss
     dev = torch.device("cuda:0")
-    spec = PassSpec(layers=[2] + [256] * 9 + [3], kind="continuity_only", dirs={"x": 0, "y": 1},
-                    fields={"U": 0, "V": 1, "h": 2}, target_cols=[0, 1], precision="tf32")
-    with pytest.raises(RuntimeError, match="tf32|hidden"):
-        JetLoss(spec, torch.zeros(8, 2, device=dev), torch.zeros(8, 2, device=dev))
+    layers = [2] + [256] * 11 + [3]
+    kw = dict(kind="continuity_only", dirs={"x": 0, "y": 1}, fields={"U": 0, "V": 1, "h": 2}, target_cols=[0, 1])
+    flat = torch.from_numpy(jo.make_params(layers, 1234, "tanh", np.float32)).to(dev)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    n = 1000
+    X = (torch.rand(n, 2, generator=g) * 2 - 1).to(dev)
+    T = (0.05 * torch.randn(n, 2, generator=g)).to(dev)
+    res = {}
+    for p in ("fp32", prec):
+        jl = JetLoss(PassSpec(layers=layers, precision=p, **kw), X, T)
+        grad = torch.empty_like(flat)
+        parts = jl.loss_and_grad(flat, grad).clone()
+        torch.cuda.synchronize()
+        res[p] = (parts, grad)
+    assert torch.isfinite(res[prec][1]).all()
+    assert abs(res[prec][0][2].item() - res["fp32"][0][2].item()) <= lt * abs(res["fp32"][0][2].item())
+    assert ((res[prec][1] - res["fp32"][1]).norm() / res["fp32"][1].norm()).item() <= gt
+    # every hidden bias gradient individually (the staged ones and the direct ones)
+    H = 256
+    off = 2 * H + H
+    for hl in range(10):
+        sl = slice(off + hl * (H * H + H) + H * H, off + (hl + 1) * (H * H + H))
+        a, b = res[prec][1][sl], res["fp32"][1][sl]
+        assert ((a - b).norm() / b.norm()).item() <= 4 * gt, hl
 
 
 @pytest.mark.parametrize("hidden", [2, 5])
