@@ -45,7 +45,11 @@ enum {
   PINN_RES_CONT_FTEMP = 2, /* physics.py:37-47  continuity_ftemp(x,y,h,U,V)     dirs (x,y)          */
   PINN_RES_NSWE = 3,       /* physics.py:50-88  Navier_Stokes(t,x,y,h,z,u,v)    dirs (t,x,y)        */
   PINN_RES_WAVE_AVG = 4,   /* physics.py:91-120 physics_equation(x,y,h,U,V,eta_mean,Hrms,k) (x,y)   */
-  PINN_RES_EXTERNAL = 5    /* caller supplies d loss/d(out), d loss/d(out_j) (autograd facade)      */
+  PINN_RES_EXTERNAL = 5,   /* caller supplies d loss/d(out), d loss/d(out_j) (autograd facade)      */
+  /* the historical physics_functions module (__pycache__/physics_functions.cpython-38.pyc, decompiled):     */
+  PINN_RES_BOUSSINESQ = 6, /* :55-130 Boussinesq(output,t,x,y,device): fully nonlinear, input derivatives up  */
+                           /*         to THIRD order -- order-3 Taylor jets (csrc/jet3.cu); dirs (t,x,y)      */
+  PINN_RES_BOUSS_SIMPLE = 7 /* :18-52 Boussinesq_simple(output,t,x,y,device): first order; dirs (t,x,y)       */
 };
 
 /* arithmetic of the per-layer contractions */
@@ -74,7 +78,7 @@ enum {
  * dir_cols[j]   input column differentiated for direction j; direction order is the physics
  *               function's argument order: (x,y) or (t,x,y)
  * field_cols[f] output column of field f; field order is the physics function's argument order:
- *               CONT_*: (h,U,V)   NSWE: (h,z,u,v)   WAVE_AVG: (h,U,V,eta_mean,Hrms,k)
+ *               CONT_*: (h,U,V)   NSWE, BOUSS*: (h,z,u,v)   WAVE_AVG: (h,U,V,eta_mean,Hrms,k)
  * mask_col      input column that continuity_only compares with cond_threshold (physics.py:27)
  * target_cols[i] output column supervised by targets[:,i], weight target_w[i]
  *               (train.py:136-141; weight 1 in train_newmethod.py:129-133)

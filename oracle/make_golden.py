@@ -80,6 +80,17 @@ CASES = {
                     dirs={"x": 0, "y": 1},
                     fields={"h": 0, "U": 1, "V": 2, "eta_mean": 3, "Hrms": 4, "k": 5},
                     target_cols=[0, 1, 2, 3, 4, 5], zero_out_cols=[5], n=64, n_fid=12, form="two_pass"),
+    # the historical physics_functions residuals (bytecode only in the reference; the "reference run" for these three is
+    # oracle/boussinesq_oracle.py = the decompiled functions re-typed, under torch autograd: see run_reference)
+    "bouss": dict(layers=[3] + [20] * 6 + [4], activation="tanh", kind="Boussinesq",
+                  dirs={"t": 0, "x": 1, "y": 2}, fields={"h": 0, "z": 1, "u": 2, "v": 3},
+                  target_cols=[0, 1, 2, 3], n=90, form="single"),
+    "bouss_wide": dict(layers=[4] + [64] * 3 + [4], activation="tanh", kind="Boussinesq",
+                       dirs={"t": 0, "x": 1, "y": 2}, fields={"h": 0, "z": 1, "u": 2, "v": 3},
+                       target_cols=[2, 3], n=41, form="single", w_fid=0.5, w_res=2.0),
+    "bouss_simple": dict(layers=[3] + [16] * 4 + [4], activation="tanh", kind="Boussinesq_simple",
+                         dirs={"t": 0, "x": 1, "y": 2}, fields={"h": 0, "z": 1, "u": 2, "v": 3},
+                         target_cols=[0, 1, 2, 3], n=150, form="single"),
     # odd widths (not multiples of 4) and a ragged tile
     "ragged": dict(layers=[3, 7, 13, 5, 4], activation="tanh", kind=jo.NSWE,
                    dirs={"t": 0, "x": 1, "y": 2}, fields={"h": 3, "z": 0, "u": 2, "v": 1},
@@ -109,8 +120,26 @@ def _flat_grad(model):
     return torch.cat([p.grad.reshape(-1) for p in model.parameters()]).detach().numpy().copy()
 
 
+def run_decompiled(case, dtype):
+    """Boussinesq / Boussinesq_simple: the reference module exists only as Python-3.8 bytecode and cannot be imported here;
+    the decompiled functions (oracle/boussinesq_oracle.py) are run under torch autograd instead."""
+    from . import boussinesq_oracle as bo
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    flat = jo.make_case_params(case, dtype)
+    d, nt = case["layers"][0], len(case["target_cols"])
+    X, T = jo.make_points(case["n"], d, nt, seed=1234)
+    spec = dict(layers=case["layers"], activation=case["activation"], kind=case["kind"], dirs=case["dirs"],
+                target_cols=case["target_cols"], w_fid=case.get("w_fid", 1.0), w_res=case.get("w_res", 1.0))
+    r = bo.loss_and_grad(spec, torch.from_numpy(flat).to(tdt), torch.from_numpy(X.astype(dtype)).to(tdt),
+                         torch.from_numpy(T.astype(dtype)).to(tdt))
+    return dict(loss=float(r["loss"]), fidelity=float(r["fidelity"]), residual=float(r["residual"]),
+                grad=r["grad"].numpy().copy(), out=r["out"].numpy().copy())
+
+
 def run_reference(case, dtype):
     """Evaluate loss + gradient exactly the way the reference's loss_func does."""
+    if case["kind"] in ("Boussinesq", "Boussinesq_simple"):
+        return run_decompiled(case, dtype)
     ref_dnn, ref_physics = _ref_modules()
     tdt = torch.float64 if dtype == np.float64 else torch.float32
     layers = case["layers"]

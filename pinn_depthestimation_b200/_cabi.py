@@ -11,7 +11,7 @@ import os
 MAX_LINEAR, MAX_OUT, MAX_DIRS, NSUMS = 128, 8, 3, 16
 
 ACT = {"tanh": 0, "leaky_relu": 1}
-RES_NONE, RES_CONT_ONLY, RES_CONT_FTEMP, RES_NSWE, RES_WAVE_AVG, RES_EXTERNAL = range(6)
+RES_NONE, RES_CONT_ONLY, RES_CONT_FTEMP, RES_NSWE, RES_WAVE_AVG, RES_EXTERNAL, RES_BOUSSINESQ, RES_BOUSS_SIMPLE = range(8)
 PREC = {"fp32": 0, "tf32": 1, "tf32x3": 2}
 FLAG_ACCUMULATE, FLAG_SKIP_PACK = 1, 2
 SUM_FC, SUM_FX, SUM_FY, SUM_COND, SUM_MASKCNT, SUM_TARGET0, SUM_NPOINTS = 0, 1, 2, 3, 4, 5, 13

@@ -550,7 +550,7 @@ __global__ void finalize_kernel(const __grid_constant__ pinn_desc_t D, const dou
   double res = 0.0;
   const int k = D.residual_kind;
   if (k == PINN_RES_CONT_ONLY || k == PINN_RES_CONT_FTEMP) res = v[PINN_SUM_FC] / (double)n_res;
-  if (k == PINN_RES_NSWE || k == PINN_RES_WAVE_AVG)
+  if (k == PINN_RES_NSWE || k == PINN_RES_WAVE_AVG || k == PINN_RES_BOUSSINESQ || k == PINN_RES_BOUSS_SIMPLE)
     res = v[PINN_SUM_FC] / (double)n_res + v[PINN_SUM_FX] / (double)n_res +
           v[PINN_SUM_FY] / (double)n_res;
   if (k == PINN_RES_CONT_ONLY) {
@@ -571,7 +571,14 @@ int tc_workspace(const pinn_desc_t* D, long long n_points, int sms, size_t* pack
 int run_tc_pass(const pinn_desc_t* D, const pinn_eval_args_t* a, bool bwd, void* workspace, size_t ws_bytes,
                 cudaStream_t st);
 
-static bool is_residual_kind(int k) { return k >= PINN_RES_CONT_ONLY && k <= PINN_RES_WAVE_AVG; }
+// jet3.cu
+bool jet3_supported(const pinn_desc_t* D, const char** why);
+int jet3_workspace(const pinn_desc_t* D, long long n_points, bool bwd, size_t* bytes, int* grid_out, long long* stride_out,
+                   int* wmax_out);
+int run_jet3_pass(const pinn_desc_t* D, const pinn_eval_args_t* a, bool bwd, cudaStream_t st);
+
+// residual kinds the first-order kernels evaluate (BOUSSINESQ needs third-order jets: jet3.cu)
+static bool is_residual_kind(int k) { return (k >= PINN_RES_CONT_ONLY && k <= PINN_RES_WAVE_AVG) || k == PINN_RES_BOUSS_SIMPLE; }
 
 // Which kernel runs this pass?  TF32 is only defined for PDE-residual passes of 256-wide tanh nets; value-only
 // (fidelity) and external-seed passes always use the FP32 kernel.  Anything else asked for in TF32 is an error.
@@ -601,7 +608,9 @@ static int jets_for(const pinn_desc_t* D) {
     case PINN_RES_CONT_ONLY:
     case PINN_RES_CONT_FTEMP:
     case PINN_RES_WAVE_AVG: return 3;
-    case PINN_RES_NSWE: return 4;
+    case PINN_RES_NSWE:
+    case PINN_RES_BOUSSINESQ:
+    case PINN_RES_BOUSS_SIMPLE: return 4;
     case PINN_RES_EXTERNAL: return 1 + D->n_dirs;
   }
   return -1;
@@ -619,14 +628,15 @@ int validate_desc(const pinn_desc_t* D) {
   if (D->activation != PINN_ACT_TANH && D->activation != PINN_ACT_LEAKY_RELU)
     return set_error("unknown activation %d", D->activation), PINN_E_ARG;
   const int k = D->residual_kind;
-  if (k < PINN_RES_NONE || k > PINN_RES_EXTERNAL) return set_error("unknown residual kind %d", k), PINN_E_ARG;
-  const int want_dirs = (k == PINN_RES_NONE) ? 0 : (k == PINN_RES_NSWE) ? 3 : (k == PINN_RES_EXTERNAL) ? D->n_dirs : 2;
+  if (k < PINN_RES_NONE || k > PINN_RES_BOUSS_SIMPLE) return set_error("unknown residual kind %d", k), PINN_E_ARG;
+  const bool txy = k == PINN_RES_NSWE || k == PINN_RES_BOUSSINESQ || k == PINN_RES_BOUSS_SIMPLE;
+  const int want_dirs = (k == PINN_RES_NONE) ? 0 : txy ? 3 : (k == PINN_RES_EXTERNAL) ? D->n_dirs : 2;
   if (D->n_dirs != want_dirs || D->n_dirs < 0 || D->n_dirs > PINN_MAX_DIRS)
     return set_error("residual kind %d needs %d differentiated directions, got %d", k, want_dirs, D->n_dirs), PINN_E_ARG;
   for (int j = 0; j < D->n_dirs; ++j)
     if (D->dir_cols[j] < 0 || D->dir_cols[j] >= D->widths[0])
       return set_error("dir_cols[%d]=%d is not an input column", j, D->dir_cols[j]), PINN_E_ARG;
-  const int nf = (k == PINN_RES_CONT_ONLY || k == PINN_RES_CONT_FTEMP) ? 3 : (k == PINN_RES_NSWE) ? 4 : (k == PINN_RES_WAVE_AVG) ? 6 : 0;
+  const int nf = (k == PINN_RES_CONT_ONLY || k == PINN_RES_CONT_FTEMP) ? 3 : txy ? 4 : (k == PINN_RES_WAVE_AVG) ? 6 : 0;
   for (int f = 0; f < nf; ++f) {
     if (D->field_cols[f] < 0 || D->field_cols[f] >= D->widths[L])
       return set_error("field_cols[%d]=%d is not an output column", f, D->field_cols[f]), PINN_E_ARG;
@@ -739,6 +749,11 @@ int workspace_bytes(const pinn_desc_t* D, long long n_points, bool bwd, size_t* 
   Config c;
   int rc = validate_desc(D);
   if (rc) return rc;
+  if (D->residual_kind == PINN_RES_BOUSSINESQ) {
+    const char* why = "";
+    if (!jet3_supported(D, &why)) return set_error("Boussinesq residual: %s", why), PINN_E_UNSUPPORTED;
+    return jet3_workspace(D, n_points, bwd, bytes, nullptr, nullptr, nullptr);
+  }
   bool tc = false;
   rc = uses_tc(D, &tc);
   if (rc) return rc;
@@ -772,7 +787,7 @@ int run_pass(const pinn_desc_t* D, const pinn_eval_args_t* a, bool bwd, cudaStre
   if (bwd && !a->grad) return set_error("grad must be non-NULL for fwdbwd"), PINN_E_ARG;
   if (D->n_targets > 0 && a->targets && a->n_fid_global <= 0)
     return set_error("n_fid_global must be positive when targets are given"), PINN_E_ARG;
-  if (D->residual_kind >= PINN_RES_CONT_ONLY && D->residual_kind <= PINN_RES_WAVE_AVG && a->n_res_global <= 0)
+  if ((is_residual_kind(D->residual_kind) || D->residual_kind == PINN_RES_BOUSSINESQ) && a->n_res_global <= 0)
     return set_error("n_res_global must be positive"), PINN_E_ARG;
   if (D->residual_kind == PINN_RES_CONT_ONLY && !a->mask_count)
     return set_error("continuity_only needs mask_count (see pinn_mask_count)"), PINN_E_ARG;
@@ -784,6 +799,15 @@ int run_pass(const pinn_desc_t* D, const pinn_eval_args_t* a, bool bwd, cudaStre
 
   long long P = 0;
   for (int i = 0; i < D->n_linear; ++i) P += (long long)D->widths[i] * D->widths[i + 1] + D->widths[i + 1];
+  if (D->residual_kind == PINN_RES_BOUSSINESQ) {
+    const char* why = "";
+    if (!jet3_supported(D, &why)) return set_error("Boussinesq residual: %s", why), PINN_E_UNSUPPORTED;
+    if (!(a->flags & PINN_FLAG_ACCUMULATE)) {
+      if (bwd) PINN_CUDA(cudaMemsetAsync(a->grad, 0, (size_t)P * 4, st));
+      if (a->sums) PINN_CUDA(cudaMemsetAsync(a->sums, 0, PINN_NSUMS * 8, st));
+    }
+    return run_jet3_pass(D, a, bwd, st);
+  }
   if (tc) {
     if (!(a->flags & PINN_FLAG_ACCUMULATE)) {
       if (bwd) PINN_CUDA(cudaMemsetAsync(a->grad, 0, (size_t)P * 4, st));

@@ -117,6 +117,37 @@ __device__ __forceinline__ void residual_epilogue(const pinn_desc_t& D, Acc& acc
       acc.add(cv, 2, ry * u);
       acc.add(cv, 3, rc * H + ry * v);
     }
+  } else if (kind == PINN_RES_BOUSS_SIMPLE) {
+    if constexpr (J >= 4) {
+      // physics_functions.py:18-52 (decompiled bytecode): f_cont = z_t + (hu)_x + (hv)_y, momentum without the breaking term
+      const int ch = D.field_cols[0], cz = D.field_cols[1], cu = D.field_cols[2], cv = D.field_cols[3];
+      const float h = acc.get(ch, 0), hx = acc.get(ch, 2), hy = acc.get(ch, 3);
+      const float zt = acc.get(cz, 1), zx = acc.get(cz, 2), zy = acc.get(cz, 3);
+      const float u = acc.get(cu, 0), ut = acc.get(cu, 1), ux = acc.get(cu, 2), uy = acc.get(cu, 3);
+      const float v = acc.get(cv, 0), vt = acc.get(cv, 1), vx = acc.get(cv, 2), vy = acc.get(cv, 3);
+      const float fc = zt + hx * u + h * ux + hy * v + h * vy;
+      const float fx = ut + u * ux + v * uy + kG * zx;
+      const float fy = vt + u * vx + v * vy + kG * zy;
+      ls[PINN_SUM_FC] = fc * fc * vf;
+      ls[PINN_SUM_FX] = fx * fx * vf;
+      ls[PINN_SUM_FY] = fy * fy * vf;
+      const float rc = wr * fc, rx = wr * fx, ry = wr * fy;
+      clear();
+      acc.add(ch, 0, rc * (ux + vy));
+      acc.add(ch, 2, rc * u);
+      acc.add(ch, 3, rc * v);
+      acc.add(cz, 1, rc);
+      acc.add(cz, 2, rx * kG);
+      acc.add(cz, 3, ry * kG);
+      acc.add(cu, 0, rc * hx + rx * ux + ry * vx);
+      acc.add(cu, 1, rx);
+      acc.add(cu, 2, rc * h + rx * u);
+      acc.add(cu, 3, rx * v);
+      acc.add(cv, 0, rc * hy + rx * uy + ry * vy);
+      acc.add(cv, 1, ry);
+      acc.add(cv, 2, ry * u);
+      acc.add(cv, 3, rc * h + ry * v);
+    }
   } else if (kind == PINN_RES_WAVE_AVG) {
     if constexpr (J >= 3) {
       const int ch = D.field_cols[0], cU = D.field_cols[1], cV = D.field_cols[2], ce = D.field_cols[3],

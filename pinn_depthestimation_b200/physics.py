@@ -92,6 +92,10 @@ class _ResidualFunction(torch.autograd.Function):
 
 def _fused(kind, dir_args, field_args):
     names_d, names_f = DIR_ORDER[kind], FIELD_ORDER[kind]
+    if len(field_args) == 1 and field_args[0].dim() == 2 and field_args[0].shape[1] >= len(names_f):
+        # physics_functions.* receive the whole DNN output and slice the columns 0..3 themselves (output[:, i:i+1])
+        out_t = field_args[0]
+        field_args = tuple(out_t[:, i:i + 1] for i in range(len(names_f)))
     src = _dnn.provenance(field_args[0])
     if src is None:
         raise RuntimeError(

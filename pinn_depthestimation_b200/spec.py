@@ -17,16 +17,21 @@ KINDS = {
     "Navier_Stokes": _cabi.RES_NSWE,            # physics.py:50-88
     "physics_equation": _cabi.RES_WAVE_AVG,     # physics.py:91-120
     "external": _cabi.RES_EXTERNAL,
+    # the historical physics_functions module (bytecode only; decompiled)
+    "Boussinesq": _cabi.RES_BOUSSINESQ,            # physics_functions.py:55-130 (third-order input derivatives)
+    "Boussinesq_simple": _cabi.RES_BOUSS_SIMPLE,   # physics_functions.py:18-52
 }
 # argument order of the physics functions = order of dir_cols / field_cols in the C desc
 DIR_ORDER = {
     "continuity_only": ("x", "y"), "continuity_ftemp": ("x", "y"),
     "Navier_Stokes": ("t", "x", "y"), "physics_equation": ("x", "y"),
+    "Boussinesq": ("t", "x", "y"), "Boussinesq_simple": ("t", "x", "y"),
 }
 FIELD_ORDER = {
     "continuity_only": ("h", "U", "V"), "continuity_ftemp": ("h", "U", "V"),
     "Navier_Stokes": ("h", "z", "u", "v"),
     "physics_equation": ("h", "U", "V", "eta_mean", "Hrms", "k"),
+    "Boussinesq": ("h", "z", "u", "v"), "Boussinesq_simple": ("h", "z", "u", "v"),
 }
 
 

@@ -100,3 +100,22 @@ def test_oracles_reproduce_the_reference_nan(name):
     tf = torch.from_numpy
     b = ap.loss_and_grad(sres, tf(flat), tf(X.astype(np.float64)), None)
     assert torch.isnan(b["residual"])
+
+
+@pytest.mark.parametrize("name", cases.BOUSS)
+def test_decompiled_boussinesq_oracle_reproduces_its_golden(name):
+    """The historical physics_functions residuals: golden = oracle/boussinesq_oracle.py (the decompiled bytecode) in float64;
+    this guards the fixture against drift of the oracle and checks float32 against north_star's bounds."""
+    from oracle import boussinesq_oracle as bo
+    case, z = cases.load(name)
+    flat, X, T, _, _ = cases.data(case, np.float32)
+    spec = dict(layers=case["layers"], activation=case["activation"], kind=case["kind"], dirs=case["dirs"],
+                target_cols=case["target_cols"], w_fid=case.get("w_fid", 1.0), w_res=case.get("w_res", 1.0))
+    tf = torch.from_numpy
+    r = bo.loss_and_grad(spec, tf(flat.astype(np.float64)), tf(X.astype(np.float64)), tf(T.astype(np.float64)))
+    assert abs(r["loss"].item() - z["loss64"]) <= 1e-12 * abs(z["loss64"])
+    assert cases.golden_grad_check(z, r["grad"].numpy()) <= 1e-11
+    if name != "bouss_wide":
+        r32 = bo.loss_and_grad(spec, tf(flat), tf(X), tf(T))
+        assert abs(r32["loss"].item() - z["loss64"]) <= 1e-5 * abs(z["loss64"])
+        assert cases.golden_grad_check(z, r32["grad"].numpy().astype(np.float64)) <= 1e-4
