@@ -1304,7 +1304,7 @@ bool tc_supported(const pinn_desc_t* D, const char** why) {
     if (D->widths[i] != TC_H) return *why = "every hidden layer must be 256 wide", false;
   if (D->activation != PINN_ACT_TANH) return *why = "tanh activation only", false;
   const int k = D->residual_kind;
-  if (k < PINN_RES_CONT_ONLY || k > PINN_RES_WAVE_AVG)
+  if ((k < PINN_RES_CONT_ONLY || k > PINN_RES_WAVE_AVG) && k != PINN_RES_BOUSS_SIMPLE)
     return *why = "needs a PDE residual kind (value-only and external-seed passes use the FP32 kernel)", false;
   return true;
 }
