@@ -570,6 +570,42 @@ def main():
                 lbfgs_real = lbfgs_run(rj, rp, 200)
                 lbfgs_real.update({"config": nm, "n_points": rn, "precision": "fp32", "ms_per_eval_alone": ms_})
 
+    # ---- the drop-in path: the body of pinn.loss_func (train_newmethod.py:120-159) + loss.backward() on dropin/{dnn,physics}.py ----
+    dropin_row = None
+    if rank == 0 and args.real_shapes:
+        sys.path.insert(0, os.path.join(ROOT, "dropin"))
+        import dnn as dropin_dnn
+        import physics as dropin_physics
+        rl, rn = [2] + [20] * 100 + [3], 12514
+        torch.manual_seed(1234)
+        mdl = dropin_dnn.DNN(rl, 0.0, "xavier").to(dev)
+        g_ = torch.Generator().manual_seed(1234)
+        xs = (torch.rand(rn, 2, generator=g_) * 2 - 1)
+        xq = xs[:, 0:1].clone().to(dev).requires_grad_(True)
+        yq = xs[:, 1:2].clone().to(dev).requires_grad_(True)
+        tq = (0.05 * torch.randn(rn, 2, generator=g_)).to(dev)
+
+        def dropin_step():
+            for p_ in mdl.parameters():
+                p_.grad = None
+            pred = mdl(torch.cat([xq, yq], dim=-1))
+            fid = sum(torch.nn.functional.mse_loss(pred[:, i:i + 1], tq[:, i:i + 1]) for i in range(2))
+            res = dropin_physics.continuity_only(xq, yq, pred[:, 2:3], pred[:, 0:1], pred[:, 1:2])
+            (fid + res).backward()
+        for _ in range(3):
+            dropin_step()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            dropin_step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_ = e0.elapsed_time(e1) / 20
+        dropin_row = {"config": "config_CMB_h.json", "n_points": rn, "ms_per_loss_func_and_backward": ms_,
+                      "points_per_s": rn / (ms_ * 1e-3),
+                      "note": "unmodified loss_func body on the drop-in modules: value forward + fused residual fwd/bwd + "
+                              "external-seed fwd/bwd for the MSE part (3 network evaluations); the fused trainer does one"}
+
     # ---- strong-scaling rows at 2^20 and 2^22 points: where the one all-reduce becomes visible ----
     scaling_rows = None
     if world > 1 and args.scaling_rows:
@@ -616,6 +652,7 @@ def main():
             "lbfgs": lbfgs_side,
             "lbfgs_real_shape": lbfgs_real,
             "lbfgs_direction": lbfgs_direction,
+            "dropin_real_shape": dropin_row,
             "real_shapes_fp32": real_shapes,
             "strong_scaling_rows": scaling_rows,
         }
