@@ -522,45 +522,91 @@ __global__ void __launch_bounds__(kVlThreads)
   __syncthreads();
   const int h2 = sh_head, m = sh_used;
   const double hdiag = V.delta[2 * cap + 1];
-  // two-loop recursion on coefficients (lbfgs.py:432-447): q = -g; logical pair i sits in slot (h2 + i) % cap
-  for (int p_ = threadIdx.x; p_ < cap; p_ += kVlThreads) dS[p_] = 0.0, dY[p_] = 0.0;
-  __shared__ double dG;
-  if (threadIdx.x == 0) dG = -1.0;
-  __syncthreads();
-  for (int i = m - 1; i >= 0; --i) {
-    const int pi = (h2 + i) % cap;
-    // s_i . q = sum_j dS_j (s_i.s_j) + dY_j (s_i.y_j) + dG (s_i.g)
-    double acc = 0.0;
-    for (int j = threadIdx.x; j < m; j += kVlThreads) {
-      const int pj = (h2 + j) % cap;
-      acc = fma(dS[pj], V.SS[(size_t)pi * cap + pj], acc);
-      acc = fma(dY[pj], V.SY[(size_t)pi * cap + pj], acc);
+  // two-loop recursion on coefficients (lbfgs.py:432-447): q = -g; logical pair i sits in slot (h2 + i) % cap.
+  // ONE warp, warp-synchronous: lane l owns the logical pairs l, l + 32, ...; the Gram row of the NEXT step is fetched while
+  // the current step is reduced, so a step costs a few FMAs and five shuffles instead of a global-memory round trip.
+  // In the backward loop q has no s components yet, so only S^T Y enters.
+  __shared__ double shS[kLbMaxHistory + 1], shY[kLbMaxHistory + 1];   // coefficients of s_p, y_p (by ring slot)
+  if (warp == 0) {
+    for (int p_ = lane; p_ < cap; p_ += 32) shS[p_] = 0.0, shY[p_] = 0.0;
+    __syncwarp();
+    double dG = -1.0;
+    constexpr int PF = 4;                       // elements per lane held in registers (m <= 128); larger m: plain loop
+    const bool pf = m <= 32 * PF;
+    double nx[PF];
+    auto slot = [&](int j) { return (h2 + j) % cap; };
+    auto fetch_sy_row = [&](int i) {            // (s_i . y_j) for this lane's j
+      const int pi = slot(i);
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const int j = lane + 32 * u;
+        nx[u] = j < m ? V.SY[(size_t)pi * cap + slot(j)] : 0.0;
+      }
+    };
+    if (pf && m > 0) fetch_sy_row(m - 1);
+    for (int i = m - 1; i >= 0; --i) {
+      const int pi = slot(i);
+      double acc = 0.0;
+      if (pf) {
+        double cur[PF];
+#pragma unroll
+        for (int u = 0; u < PF; ++u) cur[u] = nx[u];
+        if (i > 0) fetch_sy_row(i - 1);
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+          const int j = lane + 32 * u;
+          if (j < m) acc = fma(shY[slot(j)], cur[u], acc);
+        }
+      } else {
+        for (int j = lane; j < m; j += 32) acc = fma(shY[slot(j)], V.SY[(size_t)pi * cap + slot(j)], acc);
+      }
+      const double sq = vl_warp_sum(acc) + dG * dot_g_s[pi];     // s_i . q
+      const double a_i = sq / V.SY[(size_t)pi * cap + pi];       // ro_i = 1 / (y_i . s_i)
+      if (lane == 0) al[i] = a_i, shY[pi] -= a_i;
+      __syncwarp();
     }
-    const double sq = vl_block_sum(acc, warp_buf) + dG * dot_g_s[pi];
-    const double a_i = sq / V.SY[(size_t)pi * cap + pi];         // ro_i = 1 / (y_i . s_i)
-    __syncthreads();
-    if (threadIdx.x == 0) al[i] = a_i, dY[pi] -= a_i;
-    __syncthreads();
-  }
-  for (int p_ = threadIdx.x; p_ < cap; p_ += kVlThreads) dS[p_] *= hdiag, dY[p_] *= hdiag;
-  if (threadIdx.x == 0) dG *= hdiag;
-  __syncthreads();
-  for (int i = 0; i < m; ++i) {
-    const int pi = (h2 + i) % cap;
-    // y_i . r = sum_j dS_j (s_j.y_i) + dY_j (y_i.y_j) + dG (y_i.g)
-    double acc = 0.0;
-    for (int j = threadIdx.x; j < m; j += kVlThreads) {
-      const int pj = (h2 + j) % cap;
-      acc = fma(dS[pj], V.SY[(size_t)pj * cap + pi], acc);
-      acc = fma(dY[pj], V.YY[(size_t)pi * cap + pj], acc);
+    for (int p_ = lane; p_ < cap; p_ += 32) shY[p_] *= hdiag;
+    dG *= hdiag;
+    __syncwarp();
+    // forward loop: y_i . r = sum_j dS_j (s_j.y_i) + dY_j (y_i.y_j) + dG (y_i.g)
+    double nx2[PF];
+    auto fetch_fwd = [&](int i) {
+      const int pi = slot(i);
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const int j = lane + 32 * u;
+        nx[u] = j < m ? V.SY[(size_t)slot(j) * cap + pi] : 0.0;
+        nx2[u] = j < m ? V.YY[(size_t)pi * cap + slot(j)] : 0.0;
+      }
+    };
+    if (pf && m > 0) fetch_fwd(0);
+    for (int i = 0; i < m; ++i) {
+      const int pi = slot(i);
+      double acc = 0.0;
+      if (pf) {
+        double c1[PF], c2[PF];
+#pragma unroll
+        for (int u = 0; u < PF; ++u) c1[u] = nx[u], c2[u] = nx2[u];
+        if (i + 1 < m) fetch_fwd(i + 1);
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+          const int j = lane + 32 * u;
+          if (j < m) acc = fma(shS[slot(j)], c1[u], fma(shY[slot(j)], c2[u], acc));
+        }
+      } else {
+        for (int j = lane; j < m; j += 32) {
+          acc = fma(shS[slot(j)], V.SY[(size_t)slot(j) * cap + pi], acc);
+          acc = fma(shY[slot(j)], V.YY[(size_t)pi * cap + slot(j)], acc);
+        }
+      }
+      const double yr = vl_warp_sum(acc) + dG * dot_g_y[pi];
+      const double be = yr / V.SY[(size_t)pi * cap + pi];
+      if (lane == 0) shS[pi] += al[i] - be;
+      __syncwarp();
     }
-    const double yr = vl_block_sum(acc, warp_buf) + dG * dot_g_y[pi];
-    const double be = yr / V.SY[(size_t)pi * cap + pi];
-    __syncthreads();
-    if (threadIdx.x == 0) dS[pi] += al[i] - be;
-    __syncthreads();
+    for (int p_ = lane; p_ < cap; p_ += 32) dS[p_] = shS[p_], dY[p_] = shY[p_];
+    if (lane == 0) V.delta[2 * cap] = dG;
   }
-  if (threadIdx.x == 0) V.delta[2 * cap] = dG;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
