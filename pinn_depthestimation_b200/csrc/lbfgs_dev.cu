@@ -457,19 +457,54 @@ __global__ void __launch_bounds__(kVlThreads)
   const float* s_new = slot_new >= 0 ? V.S + (long long)slot_new * P : nullptr;
   const float* y_new = slot_new >= 0 ? V.Y + (long long)slot_new * P : nullptr;
   double* part = V.dots_partial + (size_t)blockIdx.x * (2 * cap) * 3;
-  for (int v = warp; v < 2 * cap; v += kVlThreads / 32) {
-    const int pslot = v < cap ? v : v - cap;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    if (vl_slot_active(pslot, head, used, cap, slot_new)) {
-      const float* vec = (v < cap ? V.S : V.Y) + (long long)pslot * P;
-      for (long long i = lo + lane; i < hi; i += 32) {
-        const double x = (double)vec[i];
-        if (s_new) a0 = fma(x, (double)s_new[i], a0), a1 = fma(x, (double)y_new[i], a1);
-        a2 = fma(x, (double)g[i], a2);
-      }
-      a0 = vl_warp_sum(a0), a1 = vl_warp_sum(a1), a2 = vl_warp_sum(a2);
+  constexpr int EL = 32;                        // elements of the slice per lane in the register-cached path
+  if (per <= 32 * EL) {
+    // the CTA's slices of s_new, y_new, g stay in registers (one coalesced load each); every stored vector then costs one
+    // load per element -- the pass is a pure stream over the 2 m P history
+    float sN[EL], yN[EL], gV[EL];
+#pragma unroll
+    for (int u = 0; u < EL; ++u) {
+      const long long i = lo + lane + 32 * u;
+      const bool in = i < hi;
+      sN[u] = (in && s_new) ? s_new[i] : 0.f;
+      yN[u] = (in && y_new) ? y_new[i] : 0.f;
+      gV[u] = in ? g[i] : 0.f;
     }
-    if (lane == 0) part[v * 3] = a0, part[v * 3 + 1] = a1, part[v * 3 + 2] = a2;
+    for (int v = warp; v < 2 * cap; v += kVlThreads / 32) {
+      const int pslot = v < cap ? v : v - cap;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+      if (vl_slot_active(pslot, head, used, cap, slot_new)) {
+        const float* vec = (v < cap ? V.S : V.Y) + (long long)pslot * P;
+        float x[EL];
+#pragma unroll
+        for (int u = 0; u < EL; ++u) {
+          const long long i = lo + lane + 32 * u;
+          x[u] = i < hi ? vec[i] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < EL; ++u) {
+          const double xd = (double)x[u];
+          a0 = fma(xd, (double)sN[u], a0), a1 = fma(xd, (double)yN[u], a1), a2 = fma(xd, (double)gV[u], a2);
+        }
+        a0 = vl_warp_sum(a0), a1 = vl_warp_sum(a1), a2 = vl_warp_sum(a2);
+      }
+      if (lane == 0) part[v * 3] = a0, part[v * 3 + 1] = a1, part[v * 3 + 2] = a2;
+    }
+  } else {
+    for (int v = warp; v < 2 * cap; v += kVlThreads / 32) {
+      const int pslot = v < cap ? v : v - cap;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+      if (vl_slot_active(pslot, head, used, cap, slot_new)) {
+        const float* vec = (v < cap ? V.S : V.Y) + (long long)pslot * P;
+        for (long long i = lo + lane; i < hi; i += 32) {
+          const double x = (double)vec[i];
+          if (s_new) a0 = fma(x, (double)s_new[i], a0), a1 = fma(x, (double)y_new[i], a1);
+          a2 = fma(x, (double)g[i], a2);
+        }
+        a0 = vl_warp_sum(a0), a1 = vl_warp_sum(a1), a2 = vl_warp_sum(a2);
+      }
+      if (lane == 0) part[v * 3] = a0, part[v * 3 + 1] = a1, part[v * 3 + 2] = a2;
+    }
   }
   if (!vl_last_cta(V.counters)) return;
 
@@ -629,6 +664,7 @@ __global__ void __launch_bounds__(kVlThreads)
   for (long long i = (long long)blockIdx.x * kVlThreads + threadIdx.x; i < P; i += (long long)gridDim.x * kVlThreads) {
     const float gi = g[i];
     double acc = cG * (double)gi;
+#pragma unroll 8
     for (int j = 0; j < m; ++j) {
       const int pj = (head + j) % cap;
       acc = fma(cS[pj], (double)V.S[(long long)pj * P + i], acc);
