@@ -210,7 +210,7 @@ typedef struct pinn_lbfgs_status {
   double t, loss, first_loss, gtd, d_norm;
 } pinn_lbfgs_status_t;
 
-int pinn_lbfgs_workspace_bytes(int64_t n_params, int32_t history_size, size_t* bytes);
+int pinn_lbfgs_workspace_bytes(int64_t n_params, int32_t history_size /* <= 512 */, size_t* bytes);
 /* Start of a step() call.  reset != 0 also clears the history and the counters (a new optimiser). */
 int pinn_lbfgs_begin(void* workspace, int64_t n_params, const pinn_lbfgs_cfg_t* cfg, int32_t reset, void* stream);
 /* grad / *loss: gradient and loss (device) of the evaluation at the current flat_params.  status_host: HOST memory

@@ -41,7 +41,7 @@ namespace pinn {
 
 constexpr int kLbCtas = 8;
 constexpr int kLbThreads = 1024;
-constexpr int kLbMaxHistory = 1024;
+constexpr int kLbMaxHistory = 512;
 
 enum { LB_PH_START = 0, LB_PH_BRACKET = 1, LB_PH_ZOOM = 2, LB_PH_DONE = 3 };
 enum { LB_STATUS_EVAL = 1, LB_STATUS_DONE = 2 };
@@ -516,6 +516,7 @@ __global__ void __launch_bounds__(kVlThreads)
   // per stored vector: its dots with s_new, y_new, g (fixed summation order over the CTAs)
   for (int v = threadIdx.x; v < 2 * cap; v += kVlThreads) {
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll 8
     for (unsigned c = 0; c < gridDim.x; ++c) {
       const double* pc = V.dots_partial + ((size_t)c * (2 * cap) + v) * 3;
       a0 += pc[0], a1 += pc[1], a2 += pc[2];
@@ -562,6 +563,9 @@ __global__ void __launch_bounds__(kVlThreads)
   // the current step is reduced, so a step costs a few FMAs and five shuffles instead of a global-memory round trip.
   // In the backward loop q has no s components yet, so only S^T Y enters.
   __shared__ double shS[kLbMaxHistory + 1], shY[kLbMaxHistory + 1];   // coefficients of s_p, y_p (by ring slot)
+  __shared__ double rho_s[kLbMaxHistory + 1];                         // ro_p = 1 / (y_p . s_p)
+  for (int p_ = threadIdx.x; p_ < cap; p_ += kVlThreads) rho_s[p_] = 1.0 / V.SY[(size_t)p_ * cap + p_];
+  __syncthreads();
   if (warp == 0) {
     for (int p_ = lane; p_ < cap; p_ += 32) shS[p_] = 0.0, shY[p_] = 0.0;
     __syncwarp();
@@ -596,7 +600,7 @@ __global__ void __launch_bounds__(kVlThreads)
         for (int j = lane; j < m; j += 32) acc = fma(shY[slot(j)], V.SY[(size_t)pi * cap + slot(j)], acc);
       }
       const double sq = vl_warp_sum(acc) + dG * dot_g_s[pi];     // s_i . q
-      const double a_i = sq / V.SY[(size_t)pi * cap + pi];       // ro_i = 1 / (y_i . s_i)
+      const double a_i = sq * rho_s[pi];
       if (lane == 0) al[i] = a_i, shY[pi] -= a_i;
       __syncwarp();
     }
@@ -635,7 +639,7 @@ __global__ void __launch_bounds__(kVlThreads)
         }
       }
       const double yr = vl_warp_sum(acc) + dG * dot_g_y[pi];
-      const double be = yr / V.SY[(size_t)pi * cap + pi];
+      const double be = yr * rho_s[pi];
       if (lane == 0) shS[pi] += al[i] - be;
       __syncwarp();
     }
@@ -691,15 +695,24 @@ __global__ void __launch_bounds__(kVlThreads)
     sp[0] = gd, sp[1] = l1, sp[2] = (double)mm;
   }
   if (!vl_last_cta(V.counters + 1)) return;
-  if (threadIdx.x != 0) return;
-  // ---------------- last CTA, one thread: lbfgs.py:449-487 ----------------
+  // ---------------- last CTA: fixed-order reduction of the partials, then one thread: lbfgs.py:449-487 ----------------
   double gtd = 0.0, g_l1 = 0.0;
   float dmax = 0.f;
-  for (unsigned c = 0; c < gridDim.x; ++c) {
+  for (unsigned c = threadIdx.x; c < gridDim.x; c += kVlThreads) {
     const double* sp = V.stats_partial + (size_t)c * 4;
     gtd += sp[0], g_l1 += sp[1];
     dmax = lb_nan_max(dmax, (float)sp[2]);
   }
+  gtd = vl_block_sum(gtd, warp_buf);
+  g_l1 = vl_block_sum(g_l1, warp_buf);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dmax = lb_nan_max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) fmax_buf[threadIdx.x >> 5] = dmax;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  dmax = 0.f;
+  for (int i = 0; i < kVlThreads / 32; ++i) dmax = lb_nan_max(dmax, fmax_buf[i]);
   LbState st = *st_g;
   st.prev_loss = st.loss;
   st.gtd = gtd;
