@@ -433,7 +433,7 @@ __device__ __forceinline__ bool vl_last_cta(unsigned* counter) {
 }
 
 __global__ void __launch_bounds__(kVlThreads)
-    vl_dots_kernel(LbState* __restrict__ st_g, LbVectors V, const float* __restrict__ g, long long P) {
+    vl_dots_kernel(LbState* __restrict__ st_g, LbVectors V, const float* __restrict__ g, long long P, int stage_bytes) {
   if (!st_g->begin) return;
   __shared__ double warp_buf[kVlThreads / 32];
   __shared__ double al[kLbMaxHistory + 1];
@@ -559,93 +559,59 @@ __global__ void __launch_bounds__(kVlThreads)
   const int h2 = sh_head, m = sh_used;
   const double hdiag = V.delta[2 * cap + 1];
   // two-loop recursion on coefficients (lbfgs.py:432-447): q = -g; logical pair i sits in slot (h2 + i) % cap.
-  // ONE warp, warp-synchronous: lane l owns the logical pairs l, l + 32, ...; the Gram row of the NEXT step is fetched while
-  // the current step is reduced, so a step costs a few FMAs and five shuffles instead of a global-memory round trip.
-  // In the backward loop q has no s components yet, so only S^T Y enters.
-  __shared__ double shS[kLbMaxHistory + 1], shY[kLbMaxHistory + 1];   // coefficients of s_p, y_p (by ring slot)
-  __shared__ double rho_s[kLbMaxHistory + 1];                         // ro_p = 1 / (y_p . s_p)
-  for (int p_ = threadIdx.x; p_ < cap; p_ += kVlThreads) rho_s[p_] = 1.0 / V.SY[(size_t)p_ * cap + p_];
+  //   backward  al_i = ro_i (s_i.q),  q -= al_i y_i      q has no s components yet, so s_i.q = sum_j cY_j (s_i.y_j) - s_i.g:
+  //             a triangular recurrence over S^T Y -- sequential, done by ONE warp from a shared-memory copy of the m x m block
+  //   r = H q;  w_i = sum_j cY_j (y_i.y_j) needs only the finished cY: a dense m x m product, all threads in parallel
+  //   forward   be_i = ro_i (y_i.r) = ro_i (sum_j cS_j (s_j.y_i) + w_i + cG y_i.g),  cS_i += al_i - be_i: triangular again
+  extern __shared__ double sy_stage[];                                // [m][m] logical block of S^T Y when it fits
+  __shared__ double cSl[kLbMaxHistory + 1], cYl[kLbMaxHistory + 1];   // coefficients of s_i, y_i (logical order)
+  __shared__ double rho_l[kLbMaxHistory + 1], wv[kLbMaxHistory + 1];
+  auto slot = [&](int j) { return (h2 + j) % cap; };
+  const bool staged = (size_t)m * m * sizeof(double) <= (size_t)stage_bytes;
+  if (staged)
+    for (int e = threadIdx.x; e < m * m; e += kVlThreads) sy_stage[e] = V.SY[(size_t)slot(e / m) * cap + slot(e % m)];
+  for (int i = threadIdx.x; i < m; i += kVlThreads) {
+    rho_l[i] = 1.0 / V.SY[(size_t)slot(i) * cap + slot(i)];           // ro_i = 1 / (y_i . s_i)
+    cSl[i] = 0.0, cYl[i] = 0.0;
+  }
+  __syncthreads();
+  auto sy = [&](int i, int j) { return staged ? sy_stage[i * m + j] : V.SY[(size_t)slot(i) * cap + slot(j)]; };   // s_i . y_j
+  double cG = -1.0;
+  if (warp == 0) {
+    for (int i = m - 1; i >= 0; --i) {
+      double acc = 0.0;
+      for (int j = i + 1 + lane; j < m; j += 32) acc = fma(cYl[j], sy(i, j), acc);   // (cY_j is still 0 for j <= i)
+      const double a_i = (vl_warp_sum(acc) + cG * dot_g_s[slot(i)]) * rho_l[i];
+      if (lane == 0) al[i] = a_i, cYl[i] = -a_i;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < m; i += kVlThreads) cYl[i] *= hdiag;
+  cG *= hdiag;
+  __syncthreads();
+  for (int i = threadIdx.x; i < m; i += kVlThreads) {
+    double acc = 0.0;
+    const double* yyr = V.YY + (size_t)slot(i) * cap;
+#pragma unroll 4
+    for (int j = 0; j < m; ++j) acc = fma(cYl[j], yyr[slot(j)], acc);
+    wv[i] = acc;
+  }
   __syncthreads();
   if (warp == 0) {
-    for (int p_ = lane; p_ < cap; p_ += 32) shS[p_] = 0.0, shY[p_] = 0.0;
-    __syncwarp();
-    double dG = -1.0;
-    constexpr int PF = 4;                       // elements per lane held in registers (m <= 128); larger m: plain loop
-    const bool pf = m <= 32 * PF;
-    double nx[PF];
-    auto slot = [&](int j) { return (h2 + j) % cap; };
-    auto fetch_sy_row = [&](int i) {            // (s_i . y_j) for this lane's j
-      const int pi = slot(i);
-#pragma unroll
-      for (int u = 0; u < PF; ++u) {
-        const int j = lane + 32 * u;
-        nx[u] = j < m ? V.SY[(size_t)pi * cap + slot(j)] : 0.0;
-      }
-    };
-    if (pf && m > 0) fetch_sy_row(m - 1);
-    for (int i = m - 1; i >= 0; --i) {
-      const int pi = slot(i);
-      double acc = 0.0;
-      if (pf) {
-        double cur[PF];
-#pragma unroll
-        for (int u = 0; u < PF; ++u) cur[u] = nx[u];
-        if (i > 0) fetch_sy_row(i - 1);
-#pragma unroll
-        for (int u = 0; u < PF; ++u) {
-          const int j = lane + 32 * u;
-          if (j < m) acc = fma(shY[slot(j)], cur[u], acc);
-        }
-      } else {
-        for (int j = lane; j < m; j += 32) acc = fma(shY[slot(j)], V.SY[(size_t)pi * cap + slot(j)], acc);
-      }
-      const double sq = vl_warp_sum(acc) + dG * dot_g_s[pi];     // s_i . q
-      const double a_i = sq * rho_s[pi];
-      if (lane == 0) al[i] = a_i, shY[pi] -= a_i;
-      __syncwarp();
-    }
-    for (int p_ = lane; p_ < cap; p_ += 32) shY[p_] *= hdiag;
-    dG *= hdiag;
-    __syncwarp();
-    // forward loop: y_i . r = sum_j dS_j (s_j.y_i) + dY_j (y_i.y_j) + dG (y_i.g)
-    double nx2[PF];
-    auto fetch_fwd = [&](int i) {
-      const int pi = slot(i);
-#pragma unroll
-      for (int u = 0; u < PF; ++u) {
-        const int j = lane + 32 * u;
-        nx[u] = j < m ? V.SY[(size_t)slot(j) * cap + pi] : 0.0;
-        nx2[u] = j < m ? V.YY[(size_t)pi * cap + slot(j)] : 0.0;
-      }
-    };
-    if (pf && m > 0) fetch_fwd(0);
     for (int i = 0; i < m; ++i) {
-      const int pi = slot(i);
       double acc = 0.0;
-      if (pf) {
-        double c1[PF], c2[PF];
-#pragma unroll
-        for (int u = 0; u < PF; ++u) c1[u] = nx[u], c2[u] = nx2[u];
-        if (i + 1 < m) fetch_fwd(i + 1);
-#pragma unroll
-        for (int u = 0; u < PF; ++u) {
-          const int j = lane + 32 * u;
-          if (j < m) acc = fma(shS[slot(j)], c1[u], fma(shY[slot(j)], c2[u], acc));
-        }
-      } else {
-        for (int j = lane; j < m; j += 32) {
-          acc = fma(shS[slot(j)], V.SY[(size_t)slot(j) * cap + pi], acc);
-          acc = fma(shY[slot(j)], V.YY[(size_t)pi * cap + slot(j)], acc);
-        }
-      }
-      const double yr = vl_warp_sum(acc) + dG * dot_g_y[pi];
-      const double be = yr * rho_s[pi];
-      if (lane == 0) shS[pi] += al[i] - be;
+      for (int j = lane; j < i; j += 32) acc = fma(cSl[j], sy(j, i), acc);           // (cS_j is still 0 for j >= i)
+      const double be = (vl_warp_sum(acc) + wv[i] + cG * dot_g_y[slot(i)]) * rho_l[i];
+      if (lane == 0) cSl[i] = al[i] - be;
       __syncwarp();
     }
-    for (int p_ = lane; p_ < cap; p_ += 32) dS[p_] = shS[p_], dY[p_] = shY[p_];
-    if (lane == 0) V.delta[2 * cap] = dG;
   }
+  __syncthreads();
+  for (int p_ = threadIdx.x; p_ < cap; p_ += kVlThreads) dS[p_] = 0.0, dY[p_] = 0.0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < m; i += kVlThreads) dS[slot(i)] = cSl[i], dY[slot(i)] = cYl[i];
+  if (threadIdx.x == 0) V.delta[2 * cap] = cG;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -785,6 +751,11 @@ static LbLayout lb_layout(long long P, int hist) {
   L.total = o;
   return L;
 }
+// dynamic shared memory of vl_dots_kernel: the m x m block of S^T Y for the coefficient recurrences (when it fits)
+static int vl_stage_bytes(int hist) {
+  const long long want = (long long)hist * hist * 8;
+  return (int)(want <= 160 * 1024 ? want : 0);
+}
 static int vl_grid(long long P) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -876,7 +847,9 @@ extern "C" int pinn_lbfgs_advance(void* workspace, int64_t n_params, int32_t his
   const long long P = (long long)n_params;
   lbfgs_advance_kernel<<<kLbCtas, kLbThreads, 0, st>>>(state, V, flat_params, grad, loss, dev_status, P);
   // the next three return at once unless the kernel above started a new outer iteration (decided on the device)
-  vl_dots_kernel<<<V.grid, kVlThreads, 0, st>>>(state, V, grad, P);
+  const int stage = vl_stage_bytes(history_size);
+  PINN_CUDA(cudaFuncSetAttribute(vl_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stage));
+  vl_dots_kernel<<<V.grid, kVlThreads, stage, st>>>(state, V, grad, P, stage);
   vl_combine_kernel<<<V.grid, kVlThreads, 0, st>>>(state, V, grad, dev_status, P);
   lbfgs_trial_kernel<<<V.grid, kVlThreads, 0, st>>>(state, V, flat_params, grad, P);
   PINN_CUDA(cudaGetLastError());
@@ -895,7 +868,9 @@ extern "C" int pinn_lbfgs_direction_probe(void* workspace, int64_t n_params, int
   LbState* state = reinterpret_cast<LbState*>(b);
   const LbVectors V = lb_vectors(workspace, n_params, history_size);
   lbfgs_probe_setup_kernel<<<1, 32, 0, st>>>(state, history_size);
-  vl_dots_kernel<<<V.grid, kVlThreads, 0, st>>>(state, V, grad, (long long)n_params);
+  const int stage = vl_stage_bytes(history_size);
+  PINN_CUDA(cudaFuncSetAttribute(vl_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stage));
+  vl_dots_kernel<<<V.grid, kVlThreads, stage, st>>>(state, V, grad, (long long)n_params, stage);
   vl_combine_kernel<<<V.grid, kVlThreads, 0, st>>>(state, V, grad, reinterpret_cast<LbStatus*>(b + L.status), (long long)n_params);
   PINN_CUDA(cudaGetLastError());
   // algorithmic bytes: both passes read the 2 m P history once; pass 1 also reads g, prev_g, d and writes the new pair,
