@@ -12,6 +12,8 @@
 //   p = point in tile; row pitch MP = J*TP + 4 floats.  A thread owns 4 points x J jets x 4 features.
 //   Weights stream through a 3-stage ring of shared-memory chunks filled by 1-D TMA bulk copies
 //   (cp.async.bulk + mbarrier complete_tx) from a packed, zero-padded copy in the workspace.
+#include <string.h>
+
 #include "common.cuh"
 #include "residual.cuh"
 
@@ -657,7 +659,13 @@ int validate_desc(const pinn_desc_t* D) {
 template <int J, int TP, int NT, bool BWD>
 static int launch_t(const pinn_desc_t* D, const KArgs& A, const Config& c, int grid, cudaStream_t st) {
   auto kern = jet_kernel<J, TP, NT, BWD>;
-  PINN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+  static size_t allowed[64] = {0};   // per instantiation and device: raising the limit is only needed when the request grows
+  int dev = 0;
+  PINN_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || c.smem > allowed[dev]) {
+    PINN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    if (dev >= 0 && dev < 64) allowed[dev] = c.smem;
+  }
   kern<<<grid, NT, c.smem, st>>>(*D, A);
   PINN_CUDA(cudaGetLastError());
   return PINN_OK;
@@ -710,7 +718,36 @@ static int launch(int J, int wclass, bool bwd, const pinn_desc_t* D, const KArgs
   PINN_DISPATCH(4, wclass, false, launch_t, D, A, c, grid, st);
 }
 
+static int make_config_uncached(const pinn_desc_t* D, bool bwd, Config* c);
+
+// The configuration (tile shape, shared memory, occupancy query) depends only on the descriptor and the device: keep the
+// last few so that the per-evaluation host path is a memcmp, not three runtime-API queries.
 int make_config(const pinn_desc_t* D, bool bwd, Config* c) {
+  if (!D) return set_error("desc is NULL"), PINN_E_ARG;
+  struct Entry {
+    pinn_desc_t d;
+    int dev, bwd, valid;
+    Config c;
+  };
+  static thread_local Entry cache[8];
+  static thread_local int next = 0;
+  int dev = 0;
+  PINN_CUDA(cudaGetDevice(&dev));
+  for (int i = 0; i < 8; ++i)
+    if (cache[i].valid && cache[i].dev == dev && cache[i].bwd == (int)bwd && memcmp(&cache[i].d, D, sizeof(pinn_desc_t)) == 0) {
+      *c = cache[i].c;
+      return PINN_OK;
+    }
+  int rc = make_config_uncached(D, bwd, c);
+  if (rc) return rc;
+  Entry& e = cache[next];
+  next = (next + 1) % 8;
+  memcpy(&e.d, D, sizeof(pinn_desc_t));
+  e.dev = dev, e.bwd = (int)bwd, e.valid = 1, e.c = *c;
+  return PINN_OK;
+}
+
+static int make_config_uncached(const pinn_desc_t* D, bool bwd, Config* c) {
   int rc = validate_desc(D);
   if (rc) return rc;
   const int J = jets_for(D);

@@ -757,8 +757,12 @@ static int vl_stage_bytes(int hist) {
   return (int)(want <= 160 * 1024 ? want : 0);
 }
 static int vl_grid(long long P) {
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static int sms = 0;          // (queried once: this sits on the per-evaluation host path)
+  if (sms == 0) {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    sms = v;
+  }
   long long g = (P + 1023) / 1024;           // at least 1024 elements per CTA
   const long long cap_g = (long long)sms * 4 < kVlMaxGrid ? (long long)sms * 4 : kVlMaxGrid;
   if (g > cap_g) g = cap_g;
@@ -811,6 +815,19 @@ __global__ void lbfgs_probe_setup_kernel(LbState* st, int hist) {
   st->max_eval = 100, st->current_evals = 1, st->loss = 1.0;
 }
 
+// opt in to the dynamic shared memory of vl_dots_kernel once per device (not on every evaluation)
+static cudaError_t vl_allow_stage(int stage) {
+  static int allowed[64] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64 || allowed[dev] < stage + 1) {
+    e = cudaFuncSetAttribute(vl_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) allowed[dev] = 160 * 1024 + 1;
+  }
+  return e;
+}
+
 }  // namespace pinn
 
 using namespace pinn;
@@ -848,7 +865,7 @@ extern "C" int pinn_lbfgs_advance(void* workspace, int64_t n_params, int32_t his
   lbfgs_advance_kernel<<<kLbCtas, kLbThreads, 0, st>>>(state, V, flat_params, grad, loss, dev_status, P);
   // the next three return at once unless the kernel above started a new outer iteration (decided on the device)
   const int stage = vl_stage_bytes(history_size);
-  PINN_CUDA(cudaFuncSetAttribute(vl_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stage));
+  PINN_CUDA(vl_allow_stage(stage));
   vl_dots_kernel<<<V.grid, kVlThreads, stage, st>>>(state, V, grad, P, stage);
   vl_combine_kernel<<<V.grid, kVlThreads, 0, st>>>(state, V, grad, dev_status, P);
   lbfgs_trial_kernel<<<V.grid, kVlThreads, 0, st>>>(state, V, flat_params, grad, P);
@@ -869,7 +886,7 @@ extern "C" int pinn_lbfgs_direction_probe(void* workspace, int64_t n_params, int
   const LbVectors V = lb_vectors(workspace, n_params, history_size);
   lbfgs_probe_setup_kernel<<<1, 32, 0, st>>>(state, history_size);
   const int stage = vl_stage_bytes(history_size);
-  PINN_CUDA(cudaFuncSetAttribute(vl_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stage));
+  PINN_CUDA(vl_allow_stage(stage));
   vl_dots_kernel<<<V.grid, kVlThreads, stage, st>>>(state, V, grad, (long long)n_params, stage);
   vl_combine_kernel<<<V.grid, kVlThreads, 0, st>>>(state, V, grad, reinterpret_cast<LbStatus*>(b + L.status), (long long)n_params);
   PINN_CUDA(cudaGetLastError());
