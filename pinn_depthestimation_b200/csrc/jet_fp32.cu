@@ -656,16 +656,25 @@ int validate_desc(const pinn_desc_t* D) {
   return PINN_OK;
 }
 
+// Opt this instantiation in to `smem` bytes of dynamic shared memory on the current device.  The limit is only ever
+// RAISED (per instantiation and device), so a cached configuration of a larger net stays launchable after a smaller one.
+template <int J, int TP, int NT, bool BWD>
+static int ensure_smem(size_t smem) {
+  static size_t allowed[64] = {0};
+  int dev = 0;
+  PINN_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || smem > allowed[dev]) {
+    PINN_CUDA(cudaFuncSetAttribute(jet_kernel<J, TP, NT, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (dev >= 0 && dev < 64) allowed[dev] = smem;
+  }
+  return PINN_OK;
+}
+
 template <int J, int TP, int NT, bool BWD>
 static int launch_t(const pinn_desc_t* D, const KArgs& A, const Config& c, int grid, cudaStream_t st) {
   auto kern = jet_kernel<J, TP, NT, BWD>;
-  static size_t allowed[64] = {0};   // per instantiation and device: raising the limit is only needed when the request grows
-  int dev = 0;
-  PINN_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || c.smem > allowed[dev]) {
-    PINN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-    if (dev >= 0 && dev < 64) allowed[dev] = c.smem;
-  }
+  int rc = ensure_smem<J, TP, NT, BWD>(c.smem);
+  if (rc) return rc;
   kern<<<grid, NT, c.smem, st>>>(*D, A);
   PINN_CUDA(cudaGetLastError());
   return PINN_OK;
@@ -674,7 +683,8 @@ static int launch_t(const pinn_desc_t* D, const KArgs& A, const Config& c, int g
 template <int J, int TP, int NT, bool BWD>
 static int occupancy_t(size_t smem, int* blocks) {
   auto kern = jet_kernel<J, TP, NT, BWD>;
-  PINN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int rc = ensure_smem<J, TP, NT, BWD>(smem);
+  if (rc) return rc;
   PINN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kern, NT, smem));
   return PINN_OK;
 }
