@@ -47,12 +47,48 @@ class pinn:
         model.eval()
         return model
 
-    @torch.no_grad()
-    def test(self, test_input_data):
-        """[N,d] normalised inputs (numpy or tensor) -> [N,o] predictions as a numpy array (test_newmethod.py:56-72)."""
+    def init_optimizers(self):
+        """test.py:44-54 / test_newmethod.py:44-54: the one-iteration L-BFGS of the optional test-time physics step."""
+        from .lbfgs import LBFGS
+        l = self.config['lbfgs_optimizer']
+        self.optimizer_LBFGS = LBFGS(self.model.parameters(), lr=l['learning_rate'], max_iter=1, max_eval=2, history_size=10,
+                                     tolerance_grad=l['tolerance_grad'], tolerance_change=l['tolerance_change'],
+                                     line_search_fn=l['line_search_fn'])
+
+    def physics_step(self, x, residual=None):
+        """test.py:91-104 (`perform_optimization`): one `optimizer_LBFGS.step(closure)` on the PDE residual over the test
+        points (no data term), as one fused evaluation per closure call."""
+        from .fused import JetLoss
+        from .spec import DIR_ORDER, FIELD_ORDER, PassSpec
+        from .train_main import residual_for_outputs
+        in_names = list(self.test_input_vars.keys())
+        out_names = list(self.config['data_test']['outputs'])
+        kind = residual or residual_for_outputs(out_names)
+        spec = PassSpec(layers=self.model.layer_sizes, activation=self.model.activation_name, kind=kind,
+                        dirs={n: in_names.index(n) for n in DIR_ORDER[kind]},
+                        fields={n: out_names.index(n) for n in FIELD_ORDER[kind]}, w_fid=0.0, w_res=1.0)
+        jl = JetLoss(spec, x, None)
+        self.init_optimizers()
+        self.model.train()
+
+        class _Closure:
+            def flat_loss_and_grad(self, fp, fg):
+                return jl.loss_and_grad(fp, fg)
+        loss = self.optimizer_LBFGS.step(_Closure())
+        self.model.eval()
+        return float(loss)
+
+    def test(self, test_input_data, perform_optimization=None, residual=None):
+        """[N,d] normalised inputs (numpy or tensor) -> [N,o] predictions as a numpy array (test_newmethod.py:56-72).
+        With config['perform_optimization'] (test.py:91) the test-time physics step runs first."""
         x = torch.as_tensor(np.ascontiguousarray(test_input_data) if not isinstance(test_input_data, torch.Tensor)
-                            else test_input_data).float().to(self.device)
-        self.test_prediction_data = self.model(x).detach().cpu().numpy()
+                            else test_input_data).float().to(self.device).contiguous()
+        if perform_optimization is None:
+            perform_optimization = bool(self.config.get('perform_optimization', False))
+        if perform_optimization:
+            self.physics_loss_before = self.physics_step(x, residual)
+        with torch.no_grad():
+            self.test_prediction_data = self.model(x).detach().cpu().numpy()
         return self.test_prediction_data
 
 

@@ -113,6 +113,14 @@ def test_prediction_dump_and_grid_inference_round_trip(tmp_path):
     flat = model.flat.detach().cpu().numpy().astype(np.float64)
     ref = jo.mlp_forward(model.layers, flat, grid.astype(np.float64))
     assert np.abs(pred - ref).max() <= 1e-5 * np.abs(ref).max()
+    # test.py:91-104: the optional test-time physics step (one L-BFGS iteration on the residual over the grid)
+    cfg2 = dict(cfg, perform_optimization=True)
+    tester2 = inference.pinn(ck, cfg2)
+    pred2 = tester2.test(grid)
+    assert pred2.shape == pred.shape and np.isfinite(pred2).all()
+    assert np.abs(pred2 - pred).max() > 0                      # the step moved the weights
+    st2 = tester2.optimizer_LBFGS.state[tester2.optimizer_LBFGS._params[0]]
+    assert st2["n_iter"] == 1 and st2["func_evals"] <= 2       # max_iter=1, max_eval=2 as in test.py:47-49
     out = str(tmp_path / "pred.mat")
     inference.export_mat(out, pred, cfg["data_test"]["outputs"])
     assert loadmat(out)["pred_h"].shape == (81 * 261, 1)
