@@ -15,6 +15,12 @@ CFG = {
                       fields={"U": 0, "V": 1, "h": 2}, target_cols=[0, 1]),
     "cmb_h": dict(layers=[2] + [20] * 100 + [3], kind="continuity_only", dirs={"x": 0, "y": 1},
                   fields={"U": 0, "V": 1, "h": 2}, target_cols=[0, 1]),
+    "bouss": dict(layers=[3] + [20] * 20 + [4], kind="Boussinesq", dirs={"t": 0, "x": 1, "y": 2},
+                  fields={"h": 0, "z": 1, "u": 2, "v": 3}, target_cols=[0, 1, 2, 3]),
+    "bouss100": dict(layers=[3] + [20] * 100 + [4], kind="Boussinesq", dirs={"t": 0, "x": 1, "y": 2},
+                     fields={"h": 0, "z": 1, "u": 2, "v": 3}, target_cols=[0, 1, 2, 3]),
+    "bouss64": dict(layers=[3] + [64] * 8 + [4], kind="Boussinesq", dirs={"t": 0, "x": 1, "y": 2},
+                    fields={"h": 0, "z": 1, "u": 2, "v": 3}, target_cols=[0, 1, 2, 3]),
     "txyz": dict(layers=[4] + [20] * 20 + [4], kind="Navier_Stokes", dirs={"t": 0, "x": 1, "y": 2},
                  fields={"h": 0, "z": 1, "u": 2, "v": 3}, target_cols=[0, 1, 2, 3]),
 }
@@ -47,6 +53,7 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.iters
 k = len(c["dirs"])
 sig = sum(c["layers"][i] * c["layers"][i + 1] for i in range(len(c["layers"]) - 1))
-flop = 6 * (1 + k) * sig * a.n
+jets = 20 if c["kind"] == "Boussinesq" else 1 + k          # third-order Taylor jets in (t, x, y): 20 coefficients
+flop = 6 * jets * sig * a.n
 print(f"{a.cfg} N={a.n} {a.precision}: {ms:.3f} ms/eval  {a.n / ms * 1e3:.4e} pts/s  "
       f"{flop / ms / 1e9:.2f} TFLOP/s  loss={parts.cpu().numpy()}")
