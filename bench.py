@@ -57,6 +57,9 @@ REAL_SHAPES = {
                     [0, 1, 2, 3], 9600),
     "config_txyz.json": ([4] + [20] * 20 + [4], "Navier_Stokes", _TXY, {"h": 0, "z": 1, "u": 2, "v": 3},
                          [0, 1, 2, 3], 9600),
+    # the historical physics_functions.Boussinesq residual (third-order input derivatives; bytecode only in the reference)
+    "physics_functions.Boussinesq": ([3] + [20] * 20 + [4], "Boussinesq", _TXY, {"h": 0, "z": 1, "u": 2, "v": 3},
+                                     [0, 1, 2, 3], 9600),
 }
 
 MODE_INFO = {
