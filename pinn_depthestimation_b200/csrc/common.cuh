@@ -44,7 +44,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
+#ifdef MBAR_TEST_WAIT
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+#endif
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(done)

@@ -76,18 +76,19 @@ constexpr int TC_THREADS = TC_WORKERS + 64;
 constexpr int TC_WCOLS = TC_H / TC_WPS;    // columns of a 128x256 accumulator owned by one worker warp
 constexpr int TC_NBLK = TC_WCOLS / 16;     // 16-column blocks per worker warp
 constexpr int TC_PARTS = TC_WORKERS / TC_H;  // worker threads per feature in the thread-per-feature phases
-constexpr int TC_STAGES = 5;
+constexpr int TC_STAGES = 5;                // ring: 5 x 16 KB (8 KB stages cost more per-stage barrier traffic than they gain)
 constexpr int TC_STAGE_BYTES = 16384;
 constexpr int TC_STAGE_FLOATS = TC_STAGE_BYTES / 4;
+constexpr int TC_CHUNK16 = 4096;            // floats per 16 KB unit of the packed weight / edge images (= two ring stages)
+constexpr int TC_PIECE = 2048;              // floats per spill piece: 16 rows x 128 features, MN-major swizzled (half a ring stage)
 constexpr int OP_LBO = TC_M * 16 + 32;     // 2080
 constexpr int OP_BYTES = (TC_H / 4) * OP_LBO;
 constexpr int TC_IMG = TC_M * TC_H;        // floats per spill image (one quantity of one layer of one tile)
 constexpr int TC_EDGE_W0 = 0;               // float offsets inside the edge block that follows the hidden-layer weight images
 constexpr int TC_EDGE_WL = TC_H * 8;        //   W0 padded [H][8] | Wlast padded [8][H] | forward-last B images [rank 2][hi,lo][4096] |
 constexpr int TC_EDGE_E1 = 2 * TC_H * 8;    //   reverse-last B images [rank 2][hi,lo][1024]   (the lo parts are used by the split-operand mode only)
-constexpr int TC_EDGE_E2 = TC_EDGE_E1 + 4 * TC_STAGE_FLOATS;
+constexpr int TC_EDGE_E2 = TC_EDGE_E1 + 4 * TC_CHUNK16;
 constexpr int TC_EDGE_FLOATS = TC_EDGE_E2 + 4 * 1024;
-constexpr int TC_GIMG = 2 * TC_IMG;        // floats per weight-gradient operand image (Zbar_l and a_{l-1} interleaved)
 constexpr int TC_WCHUNKS = TC_H * (TC_H / 2) * 4 / TC_STAGE_BYTES;   // 8 chunks per half-width weight image
 constexpr int TC_MAX_HH = 7;               // hidden->hidden layers whose bias gradients are staged in shared memory (deeper ones: global atomics)
 
@@ -226,9 +227,9 @@ __device__ __forceinline__ float tanh_approx(float x) {
   return y;
 }
 __device__ __forceinline__ float round_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  // cvt.rna.tf32.f32 (round to nearest, ties away from zero) on the sign-magnitude bit pattern: two ALU ops instead of
+  // one XU op -- the epilogues are XU-bound (tanh + 16 conversions per 16 accumulators)
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
@@ -307,7 +308,10 @@ struct TileJets {  // output jets of one point
   __device__ __forceinline__ void add(int col, int j, float v) { outs[outs_idx(row(j), col)] += v; }
 };
 
-#ifdef PINN_TC_DEBUG
+#if defined(PINN_TC_DEBUG) && !defined(PINN_TC_PHASES)
+#define PINN_TC_PHASES
+#endif
+#ifdef PINN_TC_PHASES
 #define TCT_DECL long long tct[16] = {0}; long long tct0 = clock64();
 #define TCT(i) { const long long t_ = clock64(); tct[i] += t_ - tct0; tct0 = t_; }
 #else
@@ -315,9 +319,26 @@ struct TileJets {  // output jets of one point
 #define TCT(i)
 #endif
 
-#ifdef PINN_TC_DEBUG
-__shared__ long long dbg_t_issue[8];    // producer: when the copy of a stage was issued
-__shared__ long long dbg_t_commit[8];   // issuer: when the commit releasing a stage was issued
+#ifdef KO_RING
+#define RINGWAIT(x)
+#else
+#define RINGWAIT(x) x
+#endif
+#ifdef PINN_TC_TRACE
+// event trace of ONE tile pair of cluster 0 (leader CTA): (tag, clock64) pairs, read back with pinn_debug_trace()
+__device__ long long tc_trace_buf[2 * 8192];
+__device__ int tc_trace_n;
+#define TR(tag) { if (tr_on) { tc_trace_buf[2 * (tr_base + tr_n)] = (tag); tc_trace_buf[2 * (tr_base + tr_n) + 1] = clock64(); ++tr_n; } }
+#ifdef PINN_TC_TRACE_STAGES
+#define TRS(tag) TR(tag)
+#else
+#define TRS(tag)
+#endif
+#define TR_SET(cond) tr_on = blockIdx.x == 0 && it == PINN_TC_TRACE && (cond); tr_n = 0;
+#else
+#define TR(tag)
+#define TRS(tag)
+#define TR_SET(cond)
 #endif
 template <bool BWD, bool X3>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
@@ -350,6 +371,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
+#ifdef PINN_TC_TRACE
+  bool tr_on = false;
+  int tr_n = 0;
+  const int tr_base = warp < TC_WORKERS / 32 ? 0 : (warp == TC_WORKERS / 32 ? 6144 : 512);   // workers | issuer | producer
+#endif
   const int L = D.n_linear;
   const int d = D.widths[0], o = D.widths[L];
   const int NHH = L - 2;                      // hidden->hidden layers (tensor-core jobs per direction)
@@ -404,78 +430,89 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     // =========================================== producer ===========================================
     // Both CTAs run the same load sequence; each streams ITS half of every operand:
     //   forward / adjoint job: 8 stages = the 128-column half `rank` of the weight image (32 K-features per stage)
-    //   weight-gradient job:   16 stages = for tile 0 then tile 1 of the pair, per 16 rows the 16 KB piece `rank` of G_l:
-    //                          4 panels of Zbar (A operand, its M half) and 4 panels of a_{l-1} (B operand, its N half)
-    if (lane == 0) {
-      int ps = 0, nzt = 0;
-      uint32_t pph = 1;     // parity to wait for on empty[ps] (first pass: fresh barriers count as released)
-#ifdef PINN_TC_DEBUG
-      long long d_wake = 0, d_nwake = 0;
-#endif
-      auto load_n = [&](const float* src, uint32_t bytes) {
-        mbar_wait(&empty[ps], pph);
-#ifdef PINN_TC_DEBUG
-        { const long long now = clock64(); if (dbg_t_commit[ps] > 0) { d_wake += now - dbg_t_commit[ps]; ++d_nwake; } dbg_t_issue[ps] = now; }
-#endif
-        mbar_expect_tx(&full[ps], bytes);
-        tma_load_1d(ring + ps * TC_STAGE_BYTES, src, bytes, &full[ps]);
-        if (++ps == TC_STAGES) ps = 0, pph ^= 1u;
-      };
-      auto load = [&](const float* src) { load_n(src, TC_STAGE_BYTES); };
+    //   weight-gradient job:   16 stages = for tile 0 then tile 1 of the pair, per 16 rows the piece `rank` of Zbar_l (A
+    //                          operand, its M half) and of a_{l-1} (B operand, its N half): two 8 KB copies on one barrier
+    // ONE LANE PER RING STAGE: a thread needs ~400 cycles (1,400 while the workers' spill stores and REDs fill the LSU
+    // queue) to get through wait -> expect_tx -> cp.async.bulk, whatever the copy's size (tools/mma_interf_probe.cu), so a
+    // single producer thread cannot refill faster than one stage per 400 .. 1,400 cycles; lane s owns stage s and the items
+    // s, s + S, s + 2S, ... of the load sequence, so up to S copies are being issued at once.
+    if (lane < TC_STAGES) {
+#ifndef KO_RING
       const size_t half_off = (size_t)rank * (TC_H * TC_H / 2);
-#ifdef PINN_TC_DEBUG
-      for (int q = 0; q < 8; ++q) dbg_t_commit[q] = 0;
-#endif
-      for (int it = 0; it < my_tiles; ++it) {
-        for (int hl = 0; hl < NHH; ++hl)
-          for (int c = 0; c < TC_WCHUNKS; ++c)
-            for (int x = 0; x < XP; ++x)               // (split-operand mode: the hi chunk, then the lo chunk)
-              load(A.packed + (size_t)hl * LSTRIDE + (size_t)x * LO_OFF + half_off + (size_t)c * TC_STAGE_FLOATS);
-        for (int x = 0; x < XP; ++x)                   // last layer, forward: 256 x 16 B image of this CTA
-          load(edge + TC_EDGE_E1 + (size_t)(2 * rank + x) * TC_STAGE_FLOATS);
-        if (BWD) {
-          load_n(edge + TC_EDGE_E2 + (size_t)rank * 2048, 4096 * XP);   // last layer, reverse: 8 x 128 B image(s) of this CTA
-          mbar_wait(slab_ready, (uint32_t)(it & 1));  // both tiles' activation spills are written and fenced
-          for (int l = L - 2; l >= 1; --l) {
-            for (int c = 0; c < TC_WCHUNKS; ++c)       // adjoint job of layer l
-              for (int x = 0; x < XP; ++x)
-                load(A.packed + (size_t)(l - 1) * LSTRIDE + (size_t)x * LO_OFF + (size_t)TC_H * TC_H + half_off +
-                     (size_t)c * TC_STAGE_FLOATS);
+      const int n_fwd = NHH * TC_WCHUNKS * XP;                      // items of the forward jobs
+      const int n_rev = TC_WCHUNKS * XP + 16;                       // items per reverse layer: adjoint job, weight-gradient job
+      const int per_tile = n_fwd + XP + (BWD ? 1 + NHH * n_rev : 0);
+      const long long total = (long long)my_tiles * per_tile;
+      unsigned char* stage = ring + lane * TC_STAGE_BYTES;
+      uint32_t pph = 1;     // parity to wait for on empty[lane] (first pass: fresh barriers count as released)
+      long long it = (long long)lane / per_tile;
+      int r = lane - (int)it * per_tile;                            // item r of tile pair it
+      for (long long k = lane; k < total; k += TC_STAGES, pph ^= 1u) {
+        const float* src = nullptr;
+        const float* src2 = nullptr;   // weight-gradient items: second copy (the a piece)
+        uint32_t bytes = TC_STAGE_BYTES;
+        if (r < n_fwd) {                                            // forward job of layer hl + 1, chunk c, part x (hi / lo)
+          const int hl = r / (TC_WCHUNKS * XP), q = r - hl * (TC_WCHUNKS * XP);
+          const int c = q / XP, x = q - c * XP;
+          src = A.packed + (size_t)hl * LSTRIDE + (size_t)x * LO_OFF + half_off + (size_t)c * TC_STAGE_FLOATS;
+        } else if (r < n_fwd + XP) {                                // last layer, forward: 256 x 16 B image of this CTA
+          src = edge + TC_EDGE_E1 + (size_t)(2 * rank + (r - n_fwd)) * TC_CHUNK16;
+        } else if (r == n_fwd + XP) {                               // last layer, reverse: 8 x 128 B image(s) of this CTA
+          src = edge + TC_EDGE_E2 + (size_t)rank * 2048;
+          bytes = 4096 * XP;
+        } else {
+          const int q = r - (n_fwd + XP + 1);
+          const int li = q / n_rev, w = q - li * n_rev;
+          const int l = L - 2 - li;
+          if (w < TC_WCHUNKS * XP) {                                // adjoint job of layer l
+            const int c = w / XP, x = w - c * XP;
+            src = A.packed + (size_t)(l - 1) * LSTRIDE + (size_t)x * LO_OFF + (size_t)TC_H * TC_H + half_off +
+                  (size_t)c * TC_STAGE_FLOATS;
+          } else {                                                  // weight-gradient job of layer l: tile t, 16-row chunk rr
+            const int wq = w - TC_WCHUNKS * XP, t = wq >> 3, rr = wq & 7;
+            const long long nzt = it * NHH + li;
+            mbar_wait(slab_ready, (uint32_t)(it & 1));              // both tiles' activation spills are written and fenced
             mbar_wait(&zt_ready[nzt & 1], (uint32_t)((nzt >> 1) & 1));  // Zbar_l of both tiles has been spilled
-            ++nzt;
-            for (int t = 0; t < 2; ++t) {
-              const float* gsrc = slab_pair[t] + (size_t)(l - 1) * TC_GIMG + (size_t)rank * TC_STAGE_FLOATS;
-              for (int r = 0; r < 8; ++r) load(gsrc + (size_t)r * 2 * TC_STAGE_FLOATS);
-            }
+            src = slab_pair[t] + (size_t)(NHH + (l & 1)) * TC_IMG + (size_t)(2 * rr + rank) * TC_PIECE;
+            src2 = slab_pair[t] + (size_t)(l - 1) * TC_IMG + (size_t)(2 * rr + rank) * TC_PIECE;
           }
         }
+        mbar_wait(&empty[lane], pph);
+        mbar_expect_tx(&full[lane], bytes);
+        if (src2) {
+          tma_load_1d(stage, src, TC_STAGE_BYTES / 2, &full[lane]);
+          tma_load_1d(stage + TC_STAGE_BYTES / 2, src2, TC_STAGE_BYTES / 2, &full[lane]);
+        } else {
+          tma_load_1d(stage, src, bytes, &full[lane]);
+        }
+        r += TC_STAGES;
+        while (r >= per_tile) r -= per_tile, ++it;
       }
-#ifdef PINN_TC_DEBUG
-      if (blockIdx.x == 0 && d_nwake) printf("TC producer: commit -> producer re-issue %lld cycles avg over %lld stages\n", d_wake / d_nwake, d_nwake);
 #endif
     }
-#ifdef PINN_TC_DEBUG
-    else if (lane <= TC_STAGES) {
-      // debug pollers: lane s+1 measures, for ring stage s, the time from the copy's issue to its landing
-      const int s = lane - 1;
-      const int per_tile = NHH * TC_WCHUNKS * XP + XP + (BWD ? 1 + NHH * (TC_WCHUNKS * XP + 16) : 0);
-      const long long total = (long long)my_tiles * per_tile;
-      const long long passes = (total - s + TC_STAGES - 1) / TC_STAGES;
-      long long acc = 0, mx = 0;
-      uint32_t par = 0;
-      for (long long c = 0; c < passes; ++c) {
-        mbar_wait(&full[s], par);
-        const long long dt = clock64() - dbg_t_issue[s];
-        acc += dt;
-        mx = dt > mx ? dt : mx;
-        par ^= 1u;
-      }
-      if (blockIdx.x == 0) printf("TC ring stage %d: copy issue -> landed %lld cycles avg, %lld max (%lld copies)\n", s, acc / (passes ? passes : 1), mx, passes);
-    }
-#endif
   } else if (warp == TC_WORKERS / 32 + 1) {
     // =========================================== MMA issuer =========================================
+#if defined(KO_RING)
+    if (false) {
+#elif defined(RELAY_ONE)
+    if (lane == 0 && rank != 0) {
+      // follower: relay "my stage has landed" to the leader's issuer (1-D bulk copies cannot signal a peer barrier).
+      // ONE lane, stages in ring order (the order the leader consumes them in): several lanes of one warp parked in
+      // mbarrier.try_wait on different stages delay each other.
+      const int per_tile = NHH * TC_WCHUNKS * XP + XP + (BWD ? 1 + NHH * (TC_WCHUNKS * XP + 16) : 0);
+      const long long total = (long long)my_tiles * per_tile;
+      const uint32_t fp0 = mapa_u32(&full_peer[0], 0);
+      uint32_t par = 0, st = 0;
+      for (long long c = 0; c < total; ++c) {
+        mbar_wait(&full[st], par);
+        mbar_arrive_cluster_relaxed(fp0 + 8u * st);
+        if (++st == TC_STAGES) st = 0, par ^= 1u;
+      }
+    }
+    if (false) {
+#else
     if (lane < TC_STAGES && rank != 0) {
+#endif
       // follower: relay "my stage has landed" to the leader's issuer (1-D bulk copies cannot signal a peer barrier);
       // one lane per ring stage so the hand-offs of different stages overlap
       const int per_tile = NHH * TC_WCHUNKS * XP + XP + (BWD ? 1 + NHH * (TC_WCHUNKS * XP + 16) : 0);
@@ -507,15 +544,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       uint32_t rp = 0;      // parity of the ring pass (flips every TC_STAGES chunks)
       uint32_t rs = 0;      // ring stage of the next chunk
       int jobs = 0, nB = 0;
-#ifdef PINN_TC_DEBUG
-      long long iw_ready = 0, iw_full = 0, iw_peer = 0, iw_rb = 0, i_gemm = 0, i_dw = 0, iw_full_g = 0, iw_peer_g = 0, d_lat = 0, d_nlat = 0, d_lat_dw = 0, d_nlat_dw = 0;
+#ifdef PINN_TC_PHASES
+      long long iw_ready = 0, iw_full = 0, iw_peer = 0, iw_rb = 0, i_gemm = 0, i_dw = 0, iw_full_g = 0, iw_peer_g = 0;
 #define ITM(acc, stmt) { const long long a_ = clock64(); stmt; acc += clock64() - a_; }
 #else
 #define ITM(acc, stmt) stmt;
 #endif
       // every epilogue hands the operand image over in four 64-feature slices (= two ring stages of K each)
       auto wait_slice = [&]() {
+        TRS(2640)
         ITM(iw_ready, mbar_wait(&op_ready[jobs & 3], (uint32_t)((jobs >> 2) & 1)))
+        TRS(2650)
         ++jobs;
         tc_fence_after();
       };
@@ -528,18 +567,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       // previous layer produces it (the accumulator of that layer sits in the OTHER 256 columns, so the epilogue can
       // still be reading it); otherwise all four slices are awaited first.
       auto gemm_k = [&](uint32_t dcol, bool pipelined) {
+        TR(2000)
         if (!pipelined) wait_ready();
+        TR(2100)
 #pragma unroll
         for (int c = 0; c < TC_WCHUNKS; ++c) {
           if (pipelined && (c & 1) == 0) wait_slice();
 #pragma unroll
           for (int x = 0; x < XP; ++x) {   // split-operand mode: the same operand rows against the hi, then the lo weight chunk
             const uint32_t s = rs;
-            ITM(iw_full_g, mbar_wait(&full[s], rp))
-#ifdef PINN_TC_DEBUG
-            { d_lat += clock64() - dbg_t_issue[s]; ++d_nlat; }
+            TRS(2610)
+            RINGWAIT(ITM(iw_full_g, mbar_wait(&full[s], rp)))
+            TRS(2620)
+#ifndef KO_PEER
+            RINGWAIT(ITM(iw_peer_g, mbar_wait(&full_peer[s], rp)))
 #endif
-            ITM(iw_peer_g, mbar_wait(&full_peer[s], rp))
+            TRS(2600)
             const uint64_t bd = bd_k + (uint64_t)(s * (uint32_t)STG);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
@@ -548,26 +591,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
                         idesc_k, (kstep > 0 || x > 0) ? 1u : 0u);
             }
             umma_commit(&empty[s]);
-#ifdef PINN_TC_DEBUG
-            dbg_t_commit[s] = clock64();
-#endif
+            TRS(2630)
             if (++rs == TC_STAGES) rs = 0, rp ^= 1u;
           }
         }
         umma_commit(mma_done);
+        TR(2200)
       };
       for (int it = 0; it < my_tiles; ++it) {
+        TR_SET(true)
         for (int hl = 0; hl < NHH; ++hl) {
           ITM(i_gemm, gemm_k((uint32_t)(((hl + 1) & 1) * 256), true))   // forward job of layer hl+1, accumulator (hl+1) & 1
         }
         {
-          // last layer forward: D[256 x 32] = OP * Wlast^T (columns >= o are zero), one ring stage
+          // last layer forward: D[256 x 32] = OP * Wlast^T (columns >= o are zero), one ring stage per image
           wait_ready();
 #pragma unroll
           for (int x = 0; x < XP; ++x) {
             const uint32_t s = rs;
-            ITM(iw_full_g, mbar_wait(&full[s], rp))
-            ITM(iw_peer_g, mbar_wait(&full_peer[s], rp))
+            RINGWAIT(ITM(iw_full_g, mbar_wait(&full[s], rp)))
+            RINGWAIT(ITM(iw_peer_g, mbar_wait(&full_peer[s], rp)))
             const uint64_t bd = bd_last + (uint64_t)(s * (uint32_t)STG);
 #pragma unroll
             for (int kstep = 0; kstep < TC_H / 8; ++kstep)
@@ -585,8 +628,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             ++nedge;
             tc_fence_after();
             const uint32_t s = rs;
-            ITM(iw_full_g, mbar_wait(&full[s], rp))
-            ITM(iw_peer_g, mbar_wait(&full_peer[s], rp))
+            RINGWAIT(ITM(iw_full_g, mbar_wait(&full[s], rp)))
+            RINGWAIT(ITM(iw_peer_g, mbar_wait(&full_peer[s], rp)))
             umma_tf32(tmem_base, ad_outs, bd_rl + (uint64_t)(s * (uint32_t)STG), idesc_k, 0u);
             if (X3) umma_tf32(tmem_base, ad_outs, bd_rl + (uint64_t)(s * (uint32_t)STG + 4096 / 16), idesc_k, 1u);   // lo image of W_last
             umma_commit(&empty[s]);
@@ -596,20 +639,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           // weight-gradient job of one layer into TMEM columns 256..511: both operands MN-major (contraction over
           // the 2 x 128 rows of the pair's tiles); per stage = 16 rows: [Zbar half-chunk 8 KB][A_in half-chunk 8 KB]
           auto dw_job = [&]() {
+            TR(2300)
             if (nB > 0) {
               ITM(iw_rb, mbar_wait(rb_free, (uint32_t)((nB - 1) & 1)))   // the previous accumulator has been drained in both CTAs
               tc_fence_after();
             }
             ++nB;
+            TR(2400)
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
               const uint32_t s = rs;
-              ITM(iw_full, mbar_wait(&full[s], rp))
-#ifdef PINN_TC_DEBUG
-              { d_lat_dw += clock64() - dbg_t_issue[s]; ++d_nlat_dw; }
-#endif
-              ITM(iw_peer, mbar_wait(&full_peer[s], rp))
-              const uint64_t dd = d_mn + (uint64_t)(s * (uint32_t)STG);
+              TRS(2710)
+              RINGWAIT(ITM(iw_full, mbar_wait(&full[s], rp)))
+              TRS(2720)
+              RINGWAIT(ITM(iw_peer, mbar_wait(&full_peer[s], rp)))
+              TRS(2700)
+              const uint64_t dd = d_mn + (uint64_t)(s * (uint32_t)STG);   // [Zbar piece 8 KB | a piece 8 KB]
               if (X3) {
                 // the two K atoms of a piece are the hi rows and the lo rows of the same jets: hi.hi + hi.lo + lo.hi
                 umma_tf32(tmem_base + 256u, dd, dd + 512u, idesc_mn, q > 0 ? 1u : 0u);
@@ -622,12 +667,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
                             (q > 0 || kk > 0) ? 1u : 0u);
               }
               umma_commit(&empty[s]);
-#ifdef PINN_TC_DEBUG
-              dbg_t_commit[s] = clock64();
-#endif
+              TRS(2730)
               if (++rs == TC_STAGES) rs = 0, rp ^= 1u;
             }
             umma_commit(mma_done_b);
+            TR(2500)
           };
           for (int l = L - 2; l >= 1; --l) {
             ITM(i_gemm, gemm_k(0u, false))     // adjoint of the layer input, once Zbar_l is complete in both operand images
@@ -635,10 +679,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           }
         }
       }
-#ifdef PINN_TC_DEBUG
-      if (blockIdx.x == 0)
-        printf("TC ring: copy issue -> seen full by the issuer: weights %lld cycles avg, weight-gradient operands %lld cycles avg\n",
-               d_lat / (d_nlat ? d_nlat : 1), d_lat_dw / (d_nlat_dw ? d_nlat_dw : 1));
+#ifdef PINN_TC_PHASES
       if (blockIdx.x == 0)
         printf("TC issuer (cycles per tile pair): wait op_ready %lld | fwd+adj jobs %lld (14) | dW jobs %lld (7) | gemm waits: full %lld, peer %lld | dW waits: full %lld, peer %lld, rb_free %lld\n",
                iw_ready / my_tiles, i_gemm / my_tiles, i_dw / my_tiles, iw_full_g / my_tiles, iw_peer_g / my_tiles, iw_full / my_tiles, iw_peer / my_tiles, iw_rb / my_tiles);
@@ -664,15 +705,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     // finished by all warps at the same time, so the next layer's MMA can start on slice 0 while slice 1 is computed.
     // operand image: (jet j, block b) at op_thr + 16 b * OP_LBO + j * 128
     unsigned char* op_thr = op + (4 * half + cq) * OP_LBO + mrow0 * 16;
-    // G image (Zbar part; the a part is TC_STAGE_FLOATS / 2 floats further): (j, b) at float
-    //   img_thr + (j>>1)*8192 + (j&1)*256 + (b>>1)*4096 + (2(b&1) + half/2)*512 + ((2(half&1) + cq/2) ^ (pp&3))*8
-    const int img_thr = (2 * sp) * (2 * TC_STAGE_FLOATS) + (half >> 1) * 512 + pp * 32 + (cq & 1) * 4;
+    // spill image [16-row chunk (8)][feature half (2)][piece]: (j, b) at float
+    //   img_thr + (j>>1)*4096 + (j&1)*256 + (b>>1)*2048 + (2(b&1) + half/2)*512 + ((2(half&1) + cq/2) ^ (pp&3))*8
+    const int img_thr = (2 * sp) * (2 * TC_PIECE) + (half >> 1) * 512 + pp * 32 + (cq & 1) * 4;
     const int img_swz = 2 * (half & 1) + (cq >> 1);
-    constexpr int IMG_A = TC_STAGE_FLOATS / 2;   // offset of the a_{l-1} part inside a 16 KB piece
     auto img_off = [&](int j, int b) {
-      return img_thr + (j >> 1) * (2 * TC_STAGE_FLOATS) + (j & 1) * 256 + (b >> 1) * TC_STAGE_FLOATS + (2 * (b & 1)) * 512 +
+      return img_thr + (j >> 1) * (2 * TC_PIECE) + (j & 1) * 256 + (b >> 1) * TC_PIECE + (2 * (b & 1)) * 512 +
              ((img_swz ^ (pp & 3)) << 3);
     };
+    // slab of this CTA: a_0 .. a_{L-3} (image l = a_l, the B operand of the weight-gradient job of layer l+1), then two
+    // Zbar buffers used alternately (Zbar_l in buffer l & 1): a Zbar image is dead as soon as its weight-gradient job has
+    // read it, so re-using two buffers keeps it in L2 instead of writing every layer's copy back to HBM
+    auto zbuf = [&](int l) { return slab + (size_t)(NHH + (l & 1)) * TC_IMG; };
     int nzs = 0;  // Zbar spills published
     int mj = 0;   // adjoint / forward MMA jobs waited for
     int nbw = 0;  // weight-gradient half jobs drained
@@ -689,7 +733,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     // the arrive itself is relaxed: a releasing arrive would first wait for this thread's spill stores to reach L2.
     auto signal_slice = [&]() {   // this warp's part of one 64-feature slice is written (and its TMEM reads are done)
       tc_fence_before();
+#ifndef KO_FENCE
       fence_async_proxy_smem();
+#endif
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(op_ready_leader + 8u * (uint32_t)(nsl & 3));
       ++nsl;
@@ -740,13 +786,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       }
     };
     auto st_img_block = [&](float* img, int b, const float (&v)[4][4]) {
+#ifndef KO_SPILL
 #pragma unroll
       for (int j = 0; j < 4; ++j) st_global_v4(img + img_off(j, b), v[j][0], v[j][1], v[j][2], v[j][3]);
+#endif
     };
     auto ld_img_block = [&](const float* img, int b, float (&v)[4][4]) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
+#ifdef KO_RELOAD
+        const float4 t = make_float4(0.1f, 0.2f, 0.3f, 0.4f);
+#else
         const float4 t = ld_global_v4(img + img_off(j, b));
+#endif
         v[j][0] = t.x, v[j][1] = t.y, v[j][2] = t.z, v[j][3] = t.w;
       }
     };
@@ -849,6 +901,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     };
 
     for (int it = 0; it < my_tiles; ++it) {
+      TR_SET(tid == 0)
+      TR(1900)
       const long long tile = 2ll * (pair + (long long)it * n_pairs) + rank;   // may lie past the end: an all-padding tile
       const long long p0 = tile * TP;
       for (int i = tid; i < TP * 8; i += TC_WORKERS) {
@@ -910,7 +964,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           for (int b = 0; b < TC_NBLK; ++b) {
             float z[4][4];
             ld_op_block(b, z);
-            st_img_block(slab + IMG_A, b, z);
+            st_img_block(slab, b, z);
           }
         }
       }
@@ -923,9 +977,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         for (int b = 0; b < TC_NBLK; ++b)
 #pragma unroll
           for (int i = 0; i < 4; ++i) bl[b][i] = __ldg(bias_l + 64 * b + i);
+        TR(1950 + l)
         wait_mma();
+        TR(1000 + l)
         TCT(2)
-        float* img = slab + (size_t)l * TC_GIMG + IMG_A;
+        float* img = slab + (size_t)l * TC_IMG;
         const bool spill = BWD && l <= L - 3;
 #pragma unroll
         for (int b = 0; b < TC_NBLK; ++b) {
@@ -941,6 +997,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           st_op_block(b, z);
           signal_slice();   // slice b of a_l is in the operand image: the next job (layer l+1, or 256 -> o) may consume it
         }
+        TR(1100 + l)
         if (spill) {        // spill from the operand image once all slices are handed over (see layer 0)
 #pragma unroll
           for (int b = 0; b < TC_NBLK; ++b) {
@@ -951,10 +1008,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         }
         TCT(1)
       }
+      TR(1190)
       if (BWD) publish_spill(slab_ready);
+      TR(1200)
       TCT(3)
       // ---------------- last layer (256 -> o): tensor-core job with N = 32, read back thread-per-row ----------------
       wait_mma();
+      TR(1210)
       if (half == 0) {
         const int mm = sp * 32 + lane;   // this thread's TMEM lane = tile row
         float v[8];
@@ -1005,6 +1065,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         }
       }
       worker_bar();
+      TR(1220)
       TCT(4)
       if (!BWD) continue;
       signal_edge();    // the adjoint seeds are in the output image: Abar_{L-2} = seeds * Wlast may start
@@ -1048,15 +1109,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         }
       }
       worker_bar();
+      TR(1230)
       TCT(14)
       // ---- Abar_{L-2} = seeds * W_last (tensor core), through the activation of layer L-2 -> Zbar_{L-2} in place ----
       {
-        float* zdst = slab + (size_t)(L - 3) * TC_GIMG;
+        float* zdst = zbuf(L - 2);
         // bias gradients of the first TC_MAX_HH hidden->hidden layers are staged in shared memory and flushed once at kernel
         // exit; deeper nets add the rest straight into the flat gradient (one atomic per feature per tile)
         float* dbl = (L - 3 < TC_MAX_HH) ? db_s + (size_t)(L - 3) * TC_H
                                          : A.grad + P0 + (long long)(L - 3) * PH + (long long)TC_H * TC_H;
         wait_mma();
+        TR(1300)
 #pragma unroll
         for (int b = 0; b < TC_NBLK; ++b) {
           float ab[4][4], act[4][4];
@@ -1072,7 +1135,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           else db_block(dbl, b, ab[0]);
         }
       }
+      TR(1310)
       publish_spill(&zt_ready[nzs++ & 1]);
+      TR(1320)
       TCT(5)
       // ---- hidden layers L-2 .. 1 ----
       //   tensor core: adjoint job of layer l (TMEM columns 0..255), then the weight-gradient job of layer l over the
@@ -1084,6 +1149,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         mbar_wait(mma_done_b, (uint32_t)(nbw & 1));
         ++nbw;
         tc_fence_after();
+        TR(1700 + l)
         const long long poff = P0 + (long long)(l - 1) * PH;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
@@ -1100,6 +1166,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
               for (int u = 0; u < 16; ++u) v[u] *= A.comp_dw;
             }
 #pragma unroll
+#ifdef KO_RED
+            if (v[0] == 1234.5f)
+#endif
             for (int u = 0; u < 4; ++u) {
               red_add_v2(grow + cb * 32 + 8 * u, v[4 * u], v[4 * u + 1]);
               red_add_v2(grow + 8 * TC_H + cb * 32 + 8 * u, v[4 * u + 2], v[4 * u + 3]);
@@ -1113,8 +1182,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       for (int l = L - 2; l >= 1; --l) {
         // adjoint through the activation of layer l-1 -> Zbar_{l-1} in place (+ spill for its weight gradient)
         {
-          const float* aimg = slab + (size_t)(l - 1) * TC_GIMG + IMG_A;
-          float* zdst = slab + (size_t)(l >= 2 ? l - 2 : 0) * TC_GIMG;
+          const float* aimg = slab + (size_t)(l - 1) * TC_IMG;
+          float* zdst = zbuf(l - 1);
           const int hh = l >= 2 ? l - 2 : 0;
           float* dbl = (hh < TC_MAX_HH) ? db_s + (size_t)hh * TC_H
                                         : A.grad + P0 + (long long)hh * PH + (long long)TC_H * TC_H;
@@ -1122,7 +1191,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           float act[TC_NBLK][4][4];
 #pragma unroll
           for (int b = 0; b < TC_NBLK; ++b) ld_img_block(aimg, b, act[b]);   // in flight while the adjoint MMA runs
+          TR(1350 + l)
           wait_mma();
+          TR(1400 + l)
           TCT(9)
 #pragma unroll
           for (int b = 0; b < TC_NBLK; ++b) {
@@ -1140,10 +1211,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             }
           }
         }
+        TR(1500 + l)
         TCT(10)
         if (l > 1) publish_spill(&zt_ready[nzs++ & 1]);
+        TR(1600 + l)
         TCT(6)
         drain(l);
+        TR(1800 + l)
         TCT(7)
       }
       tc_fence_before();
@@ -1181,6 +1255,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         atomicAdd(A.grad + (long long)d * TC_H + f, sb);
       }
       worker_bar();
+      TR(1990)
       TCT(12)
     }
     if (BWD) {
@@ -1191,7 +1266,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         if (hl < NHH) atomicAdd(A.grad + P0 + (long long)hl * PH + (long long)TC_H * TC_H + f, db_s[i]);
       }
     }
-#ifdef PINN_TC_DEBUG
+#ifdef PINN_TC_PHASES
     if (blockIdx.x == 0 && tid == 0) {
       long long tot = 0;
       for (int i = 0; i < 15; ++i) tot += tct[i];
@@ -1228,7 +1303,7 @@ __global__ void pack_tc_kernel(const __grid_constant__ pinn_desc_t D, const floa
   auto at = [](int n, int k) {   // float offset of B[n][k] inside its direction's two half-images
     // feature n = 16 g + 4 cq + 2 u + e sits in MMA row 16 g + 8 u + 2 cq + e (see the worker addressing)
     const int nr = (n & ~15) | (((n >> 1) & 1) << 3) | (((n >> 2) & 3) << 1) | (n & 1);
-    return (size_t)(nr >> 7) * (TC_H * TC_H / 2) + (size_t)(k >> 5) * TC_STAGE_FLOATS + (size_t)((k & 31) >> 2) * 512 +
+    return (size_t)(nr >> 7) * (TC_H * TC_H / 2) + (size_t)(k >> 5) * TC_CHUNK16 + (size_t)((k & 31) >> 2) * 512 +
            (size_t)(nr & 127) * 4 + (size_t)(k & 3);
   };
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < TC_H * TC_H; i += gridDim.x * blockDim.x) {
@@ -1259,7 +1334,7 @@ __global__ void pack_tc_kernel(const __grid_constant__ pinn_desc_t D, const floa
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
       return __uint_as_float(r);
     };
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * TC_STAGE_FLOATS; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * TC_CHUNK16; i += gridDim.x * blockDim.x) {
       if (i < TC_H * 8) {
         const int f = i >> 3, c = i & 7;
         w0p[i] = c < d ? params[(long long)f * d + c] : 0.f;
@@ -1274,16 +1349,16 @@ __global__ void pack_tc_kernel(const __grid_constant__ pinn_desc_t D, const floa
         e2[at2 + 1024] = tf32(wv - wh);
       }
       // forward image: i < 4096: rank 0, i = k * 16 + n; the rest: rank 1 = zeros
-      if (i < TC_STAGE_FLOATS) {
+      if (i < TC_CHUNK16) {
         const int k = i >> 4, n = i & 15;
         const float wv = n < o ? params[poffL + (long long)n * TC_H + k] * (x3 ? comp : 1.f) : 0.f;
         const float wh = tf32(wv);
         const size_t at1 = (size_t)(k >> 2) * 64 + n * 4 + (k & 3);
         e1[at1] = wh;
-        e1[TC_STAGE_FLOATS + at1] = tf32(wv - wh);
+        e1[TC_CHUNK16 + at1] = tf32(wv - wh);
       } else {
-        e1[TC_STAGE_FLOATS + i] = 0.f;                      // rank 1, hi
-        e1[2 * TC_STAGE_FLOATS + i] = 0.f;                  // rank 1, lo
+        e1[TC_CHUNK16 + i] = 0.f;                           // rank 1, hi
+        e1[2 * TC_CHUNK16 + i] = 0.f;                       // rank 1, lo
       }
     }
   }
@@ -1321,7 +1396,7 @@ int tc_workspace(const pinn_desc_t* D, long long n_points, int sms, size_t* pack
   long long g = 2 * pairs;   // CTA pairs (clusters of 2)
   *grid = (int)g;
   *packed_bytes = (size_t)(L - 2) * (x3 ? 4 : 2) * TC_H * TC_H * 4 + (size_t)TC_EDGE_FLOATS * 4;   // + edge-layer block
-  *slab_stride = (long long)(L - 2) * TC_GIMG;   // one weight-gradient operand image per hidden layer
+  *slab_stride = (long long)(L - 2 + 2) * TC_IMG;   // one activation image per hidden layer + two alternating Zbar buffers
   *slab_bytes = (size_t)g * (size_t)(*slab_stride) * 4;
   return PINN_OK;
 }
@@ -1379,3 +1454,14 @@ int run_tc_pass(const pinn_desc_t* D, const pinn_eval_args_t* a, bool bwd, void*
 }
 
 }  // namespace pinn
+
+#ifdef PINN_TC_TRACE
+extern "C" int pinn_debug_trace(long long* out, int max_events) {
+  cudaDeviceSynchronize();
+  const int n = max_events < 8192 ? max_events : 8192;
+  cudaMemcpyFromSymbol(out, pinn::tc_trace_buf, (size_t)n * 16);
+  static long long zeros[2 * 8192];
+  cudaMemcpyToSymbol(pinn::tc_trace_buf, zeros, sizeof(zeros));
+  return n;
+}
+#endif
