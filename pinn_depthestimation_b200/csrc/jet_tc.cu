@@ -218,6 +218,9 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float (&v)[16
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void red_add_f32(float* addr, float a) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
+}
 __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
@@ -654,16 +657,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
               TRS(2720)
               RINGWAIT(ITM(iw_peer, mbar_wait(&full_peer[s], rp)))
               TRS(2700)
-              const uint64_t dd = d_mn + (uint64_t)(s * (uint32_t)STG);   // [Zbar piece 8 KB | a piece 8 KB]
+              // stage = [Zbar piece 8 KB | a piece 8 KB]; the accumulator is the TRANSPOSED weight gradient a^T Zbar (A operand =
+              // the a piece, M = input features; B operand = the Zbar piece, N = output features), so that a TMEM lane is one
+              // input feature and the drain's warp-wide REDs hit 128 contiguous bytes of a row of dW
+              const uint64_t dz = d_mn + (uint64_t)(s * (uint32_t)STG), da = dz + 512u;
               if (X3) {
-                // the two K atoms of a piece are the hi rows and the lo rows of the same jets: hi.hi + hi.lo + lo.hi
-                umma_tf32(tmem_base + 256u, dd, dd + 512u, idesc_mn, q > 0 ? 1u : 0u);
-                umma_tf32(tmem_base + 256u, dd, dd + (uint64_t)(512 + 64), idesc_mn, 1u);
-                umma_tf32(tmem_base + 256u, dd + 64u, dd + 512u, idesc_mn, 1u);
+                // the two K atoms of a piece are the hi rows and the lo rows of the same jets: hi.hi + lo.hi + hi.lo
+                umma_tf32(tmem_base + 256u, da, dz, idesc_mn, q > 0 ? 1u : 0u);
+                umma_tf32(tmem_base + 256u, da + 64u, dz, idesc_mn, 1u);
+                umma_tf32(tmem_base + 256u, da, dz + 64u, idesc_mn, 1u);
               } else {
 #pragma unroll
                 for (int kk = 0; kk < 2; ++kk)
-                  umma_tf32(tmem_base + 256u, dd + (uint64_t)(kk * 64), dd + (uint64_t)(512 + kk * 64), idesc_mn,
+                  umma_tf32(tmem_base + 256u, da + (uint64_t)(kk * 64), dz + (uint64_t)(kk * 64), idesc_mn,
                             (q > 0 || kk > 0) ? 1u : 0u);
               }
               umma_commit(&empty[s]);
@@ -1143,37 +1149,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       //   tensor core: adjoint job of layer l (TMEM columns 0..255), then the weight-gradient job of layer l over the
       //                rows of both tiles of the pair (columns 256..511)
       //   workers:     adjoint epilogue of layer l (Zbar_{l-1} -> operand image + spill) | drain of layer l
-      // drain TMEM columns 256..511 = dW rows [128 rank, 128 rank + 128) of layer l.  16x256b loads: the 4 lanes of a
-      // quad hold 8 consecutive columns of one row, so every RED instruction updates full 32-byte sectors
+      // drain TMEM columns 256..511 = the transposed weight gradient of layer l: lane = input feature 128 rank + 32 sp + lane,
+      // column = output feature.  32x32b loads (thread = lane): for every output feature the warp adds 32 consecutive floats
+      // of one row of dW -- 128 contiguous bytes per RED instruction (tools/red_probe.cu: 7.7k cycles per 128 x 256 drain with
+      // every CTA draining at once, the L2 atomic rate; 13.2k for sector-sized v2 REDs spread over 8 rows)
       auto drain = [&](int l) {
         mbar_wait(mma_done_b, (uint32_t)(nbw & 1));
         ++nbw;
         tc_fence_after();
         TR(1700 + l)
         const long long poff = P0 + (long long)(l - 1) * PH;
+        float* gcol = A.grad + poff + (long long)cbase * TC_H + (int)rank * 128 + sp * 32 + lane;
+        const uint32_t ta = tmem_sp + (uint32_t)(256 + cbase);
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int row = (int)rank * 128 + sp * 32 + g * 16 + (lane >> 2);
-          float* grow = A.grad + poff + (long long)row * TC_H + cbase + 2 * (lane & 3);
-          const uint32_t ta = tmem_base + ((uint32_t)(sp * 32 + g * 16) << 16) + (uint32_t)(256 + cbase);
-#pragma unroll
-          for (int cb = 0; cb < TC_WCOLS / 32; ++cb) {
-            float v[16];
-            tmem_ld_16x256b_x4(ta + (uint32_t)(cb * 32), v);
-#pragma unroll
-            if (X3) {
-#pragma unroll
-              for (int u = 0; u < 16; ++u) v[u] *= A.comp_dw;
-            }
-#pragma unroll
+        for (int cb = 0; cb < TC_WCOLS / 16; ++cb) {
+          float v[16];
+          tmem_ld16(ta + (uint32_t)(cb * 16), v);
 #ifdef KO_RED
-            if (v[0] == 1234.5f)
+          if (v[0] == 1234.5f)
 #endif
-            for (int u = 0; u < 4; ++u) {
-              red_add_v2(grow + cb * 32 + 8 * u, v[4 * u], v[4 * u + 1]);
-              red_add_v2(grow + 8 * TC_H + cb * 32 + 8 * u, v[4 * u + 2], v[4 * u + 3]);
-            }
-          }
+#pragma unroll
+          for (int u = 0; u < 16; ++u)
+            red_add_f32(gcol + (long long)(cb * 16 + u) * TC_H, X3 ? v[u] * A.comp_dw : v[u]);
         }
         tc_fence_before();
         __syncwarp();

@@ -65,6 +65,19 @@ __global__ void __launch_bounds__(512, 1) red_kernel(float* G, float* Gpriv, int
       // 32768 floats per half, 512 threads x 4 floats = 2048 floats per sweep, 16 sweeps
 #pragma unroll
       for (int s = 0; s < 16; ++s) red_v4(base + (size_t)s * 2048 + tid * 4, 1.f, 1.f, 1.f, 1.f);
+    } else if (variant == 8) {
+      // scalar red, transposed accumulator: thread = column (f_in), 64 rows (f_out) per thread; a warp instruction = 128 contiguous bytes
+      float* base = G + (size_t)(half * 64) * 256 + h * 128 + sp * 32 + lane;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(base + (size_t)c * 256), "f"(1.0f) : "memory");
+    } else if (variant == 9) {
+      // v2, quad pairs own 16 consecutive columns: 8 lanes x 8 B = 64 B per row, 4 rows per instruction
+      const int row = h * 128 + sp * 32 + (lane >> 3);
+      float* grow = G + (size_t)row * 256 + cbase + 2 * (lane & 7);
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) red_v2(grow + (size_t)(4 * g) * 256 + 16 * u, 1.f, 1.f);
     } else if (variant == 4) {
       if (tid < 128) bulk_red(G + (size_t)(h * 128 + tid) * 256, stage + tid * 256, 1024);
       if (tid < 128) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -89,8 +102,9 @@ int main() {
   const int reps = 64;
   cudaFuncSetAttribute(red_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072);
   const char* names[] = {"v2 sector-complete, same order", "v2 sector-complete, CTA-rotated", "v4 thread=row (half sectors)", "v4 coalesced",
-                         "bulk reduce 1 KB rows", "v2 sector-complete, private", "v4 coalesced, private", "bulk reduce 4 KB pieces"};
-  for (int v = 0; v < 8; ++v) {
+                         "bulk reduce 1 KB rows", "v2 sector-complete, private", "v4 coalesced, private", "bulk reduce 4 KB pieces",
+                         "scalar, warp = 128 contiguous bytes", "v2, 64 B per row x 4 rows"};
+  for (int v = 0; v < 10; ++v) {
     cudaMemset(G, 0, 65536 * 4);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     red_kernel<<<148, 512, 131072>>>(G, Gp, v, 4, cyc);   // warm-up
