@@ -72,7 +72,13 @@ constexpr int TC_TP = 32;                  // points per tile (TF32 mode; the sp
 constexpr int TC_TP_X3 = 16;
 constexpr int TC_WPS = 4;                  // worker warps per TMEM subpartition
 constexpr int TC_WORKERS = 128 * TC_WPS;
-constexpr int TC_THREADS = TC_WORKERS + 64;
+constexpr int TC_THREADS = TC_WORKERS + 128;   // 16 worker warps + one control warpgroup: producer, issuer / relay, two spare warps
+// Registers: with 20 warps every SM sub-partition holds five, so the launch bound is 96 per thread (16,384 / (5 x 32) = 102).
+// setmaxnreg moves registers inside the CTA's own allocation (640 x 96): the control warpgroup shrinks to 64 per thread
+// and hands 4 x 32 x 32 registers to the 16 worker warps, which grow to 104 (16 x 32 x 8): no spills in the epilogues and
+// room to fetch the next layer's stored activations before the drain.
+constexpr int TC_WORKER_REGS = 104;
+constexpr int TC_CONTROL_REGS = 64;
 constexpr int TC_WCOLS = TC_H / TC_WPS;    // columns of a 128x256 accumulator owned by one worker warp
 constexpr int TC_NBLK = TC_WCOLS / 16;     // 16-column blocks per worker warp
 constexpr int TC_PARTS = TC_WORKERS / TC_H;  // worker threads per feature in the thread-per-feature phases
@@ -160,6 +166,22 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// same, descriptors as (low word, high word): only the low word (start address, LBO) varies per MMA, so the issue loop does
+// 32-bit arithmetic and keeps two high words for all jobs -- the issuer runs in a 64-register warpgroup
+__device__ __forceinline__ void umma_tf32_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // arrive on the mbarrier at this shared-memory offset in BOTH CTAs of the pair when all previously issued MMAs
@@ -429,6 +451,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  if (warp >= TC_WORKERS / 32) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_CONTROL_REGS));
+  // (warps 18, 19: spare warps of the control warpgroup -- setmaxnreg works on whole warpgroups)
   if (warp == TC_WORKERS / 32) {
     // =========================================== producer ===========================================
     // Both CTAs run the same load sequence; each streams ITS half of every operand:
@@ -538,12 +563,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       // built once; per MMA only the 14-bit start-address field (16-byte units) advances by a compile-time
       // constant; the ring stage index is a small running counter.
       const uint64_t ad_op = umma_desc(smem_u32(op), OP_LBO, 128);            // + kstep * (2 * OP_LBO / 16)
-      const uint64_t bd_k = umma_desc(smem_u32(ring), (TC_H / 2) * 16, 128);  // K-major half-width weight chunk in stage 0
-      const uint64_t d_mn = umma_desc_mn(smem_u32(ring), 2048, 512);          // MN-major spill half-chunk in stage 0
+      const uint64_t bd_k = umma_desc(smem_u32(ring), (TC_H / 2) * 16, 128);  // K-major half-width weight chunk in stage 0; also the
+                                                                              // [2][128 rows][4] reverse last-layer image
+      const uint64_t d_mn = umma_desc_mn(smem_u32(ring), 2048, 512);          // MN-major spill piece in stage 0
       const uint64_t bd_last = umma_desc(smem_u32(ring), 16 * 16, 128);       // [k/4][16 rows][4] last-layer image in stage 0
-      const uint64_t bd_rl = umma_desc(smem_u32(ring), (TC_H / 2) * 16, 128); // [2][128 rows][4] reverse last-layer image
       const uint64_t ad_outs = umma_desc(smem_u32(outs), TC_M * 16, 128);     // [2][128 rows][4] adjoint seeds (K = 8 outputs)
-      constexpr uint64_t STG = TC_STAGE_BYTES / 16;
+      const uint32_t hi_k = (uint32_t)(ad_op >> 32), hi_mn = (uint32_t)(d_mn >> 32);   // (all K-major descriptors share SBO = 128)
+      const uint32_t op_lo = (uint32_t)ad_op, ring_lo = (uint32_t)bd_k, last_lo = (uint32_t)bd_last, outs_lo = (uint32_t)ad_outs;
+      constexpr uint32_t STG = TC_STAGE_BYTES / 16;
       uint32_t rp = 0;      // parity of the ring pass (flips every TC_STAGES chunks)
       uint32_t rs = 0;      // ring stage of the next chunk
       int jobs = 0, nB = 0;
@@ -573,7 +600,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         TR(2000)
         if (!pipelined) wait_ready();
         TR(2100)
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < TC_WCHUNKS; ++c) {
           if (pipelined && (c & 1) == 0) wait_slice();
 #pragma unroll
@@ -586,13 +613,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             RINGWAIT(ITM(iw_peer_g, mbar_wait(&full_peer[s], rp)))
 #endif
             TRS(2600)
-            const uint64_t bd = bd_k + (uint64_t)(s * (uint32_t)STG);
+            const uint32_t b_lo = ring_lo + s * STG, a_lo = op_lo + (uint32_t)c * (4 * (2 * OP_LBO / 16));
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const int kstep = c * 4 + kk;  // 8 contraction features per MMA = two 16-byte K chunks
-              umma_tf32(tmem_base + dcol, ad_op + (uint64_t)(kstep * (2 * OP_LBO / 16)), bd + (uint64_t)(kk * (2 * (TC_H / 2) * 16 / 16)),
-                        idesc_k, (kstep > 0 || x > 0) ? 1u : 0u);
-            }
+            for (int kk = 0; kk < 4; ++kk)   // 8 contraction features per MMA = two 16-byte K chunks
+              umma_tf32_lh(tmem_base + dcol, a_lo + (uint32_t)(kk * (2 * OP_LBO / 16)), hi_k, b_lo + (uint32_t)(kk * (2 * (TC_H / 2) * 16 / 16)), hi_k,
+                           idesc_k, (c > 0 || kk > 0 || x > 0) ? 1u : 0u);
             umma_commit(&empty[s]);
             TRS(2630)
             if (++rs == TC_STAGES) rs = 0, rp ^= 1u;
@@ -614,11 +639,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             const uint32_t s = rs;
             RINGWAIT(ITM(iw_full_g, mbar_wait(&full[s], rp)))
             RINGWAIT(ITM(iw_peer_g, mbar_wait(&full_peer[s], rp)))
-            const uint64_t bd = bd_last + (uint64_t)(s * (uint32_t)STG);
-#pragma unroll
+            const uint32_t b_lo = last_lo + s * STG;
+#pragma unroll 4
             for (int kstep = 0; kstep < TC_H / 8; ++kstep)
-              umma_tf32(tmem_base, ad_op + (uint64_t)(kstep * (2 * OP_LBO / 16)), bd + (uint64_t)(kstep * (2 * 16 * 16 / 16)), idesc_last,
-                        (kstep > 0 || x > 0) ? 1u : 0u);
+              umma_tf32_lh(tmem_base, op_lo + (uint32_t)(kstep * (2 * OP_LBO / 16)), hi_k, b_lo + (uint32_t)(kstep * (2 * 16 * 16 / 16)), hi_k, idesc_last,
+                           (kstep > 0 || x > 0) ? 1u : 0u);
             umma_commit(&empty[s]);
             if (++rs == TC_STAGES) rs = 0, rp ^= 1u;
           }
@@ -633,8 +658,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             const uint32_t s = rs;
             RINGWAIT(ITM(iw_full_g, mbar_wait(&full[s], rp)))
             RINGWAIT(ITM(iw_peer_g, mbar_wait(&full_peer[s], rp)))
-            umma_tf32(tmem_base, ad_outs, bd_rl + (uint64_t)(s * (uint32_t)STG), idesc_k, 0u);
-            if (X3) umma_tf32(tmem_base, ad_outs, bd_rl + (uint64_t)(s * (uint32_t)STG + 4096 / 16), idesc_k, 1u);   // lo image of W_last
+            umma_tf32_lh(tmem_base, outs_lo, hi_k, ring_lo + s * STG, hi_k, idesc_k, 0u);
+            if (X3) umma_tf32_lh(tmem_base, outs_lo, hi_k, ring_lo + s * STG + 4096 / 16, hi_k, idesc_k, 1u);   // lo image of W_last
             umma_commit(&empty[s]);
             if (++rs == TC_STAGES) rs = 0, rp ^= 1u;
             umma_commit(mma_done);
@@ -649,7 +674,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             }
             ++nB;
             TR(2400)
-#pragma unroll
+#pragma unroll 1
             for (int q = 0; q < 16; ++q) {
               const uint32_t s = rs;
               TRS(2710)
@@ -660,17 +685,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
               // stage = [Zbar piece 8 KB | a piece 8 KB]; the accumulator is the TRANSPOSED weight gradient a^T Zbar (A operand =
               // the a piece, M = input features; B operand = the Zbar piece, N = output features), so that a TMEM lane is one
               // input feature and the drain's warp-wide REDs hit 128 contiguous bytes of a row of dW
-              const uint64_t dz = d_mn + (uint64_t)(s * (uint32_t)STG), da = dz + 512u;
+              const uint32_t dz = ring_lo + s * STG, da = dz + 512u;
               if (X3) {
                 // the two K atoms of a piece are the hi rows and the lo rows of the same jets: hi.hi + lo.hi + hi.lo
-                umma_tf32(tmem_base + 256u, da, dz, idesc_mn, q > 0 ? 1u : 0u);
-                umma_tf32(tmem_base + 256u, da + 64u, dz, idesc_mn, 1u);
-                umma_tf32(tmem_base + 256u, da, dz + 64u, idesc_mn, 1u);
+                umma_tf32_lh(tmem_base + 256u, da, hi_mn, dz, hi_mn, idesc_mn, q > 0 ? 1u : 0u);
+                umma_tf32_lh(tmem_base + 256u, da + 64u, hi_mn, dz, hi_mn, idesc_mn, 1u);
+                umma_tf32_lh(tmem_base + 256u, da, hi_mn, dz + 64u, hi_mn, idesc_mn, 1u);
               } else {
 #pragma unroll
                 for (int kk = 0; kk < 2; ++kk)
-                  umma_tf32(tmem_base + 256u, da + (uint64_t)(kk * 64), dz + (uint64_t)(kk * 64), idesc_mn,
-                            (q > 0 || kk > 0) ? 1u : 0u);
+                  umma_tf32_lh(tmem_base + 256u, da + (uint32_t)(kk * 64), hi_mn, dz + (uint32_t)(kk * 64), hi_mn, idesc_mn,
+                               (q > 0 || kk > 0) ? 1u : 0u);
               }
               umma_commit(&empty[s]);
               TRS(2730)
@@ -691,8 +716,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
                iw_ready / my_tiles, i_gemm / my_tiles, i_dw / my_tiles, iw_full_g / my_tiles, iw_peer_g / my_tiles, iw_full / my_tiles, iw_peer / my_tiles, iw_rb / my_tiles);
 #endif
     }
+  }
   } else {
     // =========================================== workers ============================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_WORKER_REGS));
     const int sp = warp & 3, half = warp >> 2;   // the four warps of a subpartition split every 64-feature slice
     const int cbase = half * TC_WCOLS;           // (drain only: contiguous column range of this warp)
     const int pp = lane >> 2, cq = lane & 3;     // point within the subpartition, column pair within 8 columns
@@ -1176,18 +1203,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster_relaxed(rb_free_leader);   // (a releasing arrive would wait for the REDs)
       };
+      // the stored activations a_{l-1} the adjoint epilogue of layer l needs are fetched one layer ahead, BEFORE the drain of
+      // the previous layer: behind the drain's REDs the loads would sit in the LSU queue until the REDs are through
+      float act[TC_NBLK][4][4];
+#ifndef RELOAD_LATE
+#pragma unroll
+      for (int b = 0; b < TC_NBLK; ++b) ld_img_block(slab + (size_t)(L - 3) * TC_IMG, b, act[b]);
+#endif
       for (int l = L - 2; l >= 1; --l) {
         // adjoint through the activation of layer l-1 -> Zbar_{l-1} in place (+ spill for its weight gradient)
         {
-          const float* aimg = slab + (size_t)(l - 1) * TC_IMG;
           float* zdst = zbuf(l - 1);
           const int hh = l >= 2 ? l - 2 : 0;
           float* dbl = (hh < TC_MAX_HH) ? db_s + (size_t)hh * TC_H
                                         : A.grad + P0 + (long long)hh * PH + (long long)TC_H * TC_H;
           const bool hidden = l > 1;
-          float act[TC_NBLK][4][4];
+#ifdef RELOAD_LATE
 #pragma unroll
-          for (int b = 0; b < TC_NBLK; ++b) ld_img_block(aimg, b, act[b]);   // in flight while the adjoint MMA runs
+          for (int b = 0; b < TC_NBLK; ++b) ld_img_block(slab + (size_t)(l - 1) * TC_IMG, b, act[b]);   // in flight while the adjoint MMA runs
+#endif
           TR(1350 + l)
           wait_mma();
           TR(1400 + l)
@@ -1213,6 +1247,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         if (l > 1) publish_spill(&zt_ready[nzs++ & 1]);
         TR(1600 + l)
         TCT(6)
+#ifndef RELOAD_LATE
+        if (l > 1) {
+#pragma unroll
+          for (int b = 0; b < TC_NBLK; ++b) ld_img_block(slab + (size_t)(l - 2) * TC_IMG, b, act[b]);   // a_{l-2}, for the next layer
+        }
+#endif
         drain(l);
         TR(1800 + l)
         TCT(7)
