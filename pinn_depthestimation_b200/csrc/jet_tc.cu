@@ -424,7 +424,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   // ---------------- one-time setup ----------------
   if (tid == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
+#ifdef SPLIT_FULL
       mbar_init(&full[s], 1);
+#else
+      // leader: a stage is full when its own copy has landed (the producer's expect_tx arrive + the bytes) AND the follower
+      // has relayed that its half has landed -- one barrier, one wait per stage in the issue loop
+      mbar_init(&full[s], rank == 0 ? 2 : 1);
+#endif
       mbar_init(&empty[s], 1);
       mbar_init(&full_peer[s], 1);
     }
@@ -505,6 +511,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             src2 = slab_pair[t] + (size_t)(l - 1) * TC_IMG + (size_t)(2 * rr + rank) * TC_PIECE;
           }
         }
+#ifdef KO_HALFW
+        if (!src2) bytes >>= 1;   // timing experiment: half of every weight copy (what a 4-CTA multicast would load per CTA)
+#endif
         mbar_wait(&empty[lane], pph);
         mbar_expect_tx(&full[lane], bytes);
         if (src2) {
@@ -529,7 +538,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       // mbarrier.try_wait on different stages delay each other.
       const int per_tile = NHH * TC_WCHUNKS * XP + XP + (BWD ? 1 + NHH * (TC_WCHUNKS * XP + 16) : 0);
       const long long total = (long long)my_tiles * per_tile;
+#ifdef SPLIT_FULL
       const uint32_t fp0 = mapa_u32(&full_peer[0], 0);
+#else
+      const uint32_t fp0 = mapa_u32(&full[0], 0);
+#endif
       uint32_t par = 0, st = 0;
       for (long long c = 0; c < total; ++c) {
         mbar_wait(&full[st], par);
@@ -546,7 +559,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       const int per_tile = NHH * TC_WCHUNKS * XP + XP + (BWD ? 1 + NHH * (TC_WCHUNKS * XP + 16) : 0);
       const long long total = (long long)my_tiles * per_tile;
       const long long passes = (total - lane + TC_STAGES - 1) / TC_STAGES;
+#ifdef SPLIT_FULL
       const uint32_t fp = mapa_u32(&full_peer[lane], 0);
+#else
+      const uint32_t fp = mapa_u32(&full[lane], 0);
+#endif
       uint32_t par = 0;
       for (long long c = 0; c < passes; ++c) {
         mbar_wait(&full[lane], par);
@@ -609,7 +626,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             TRS(2610)
             RINGWAIT(ITM(iw_full_g, mbar_wait(&full[s], rp)))
             TRS(2620)
-#ifndef KO_PEER
+#ifdef SPLIT_FULL
             RINGWAIT(ITM(iw_peer_g, mbar_wait(&full_peer[s], rp)))
 #endif
             TRS(2600)
@@ -638,7 +655,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           for (int x = 0; x < XP; ++x) {
             const uint32_t s = rs;
             RINGWAIT(ITM(iw_full_g, mbar_wait(&full[s], rp)))
+#ifdef SPLIT_FULL
             RINGWAIT(ITM(iw_peer_g, mbar_wait(&full_peer[s], rp)))
+#endif
             const uint32_t b_lo = last_lo + s * STG;
 #pragma unroll 4
             for (int kstep = 0; kstep < TC_H / 8; ++kstep)
@@ -657,7 +676,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             tc_fence_after();
             const uint32_t s = rs;
             RINGWAIT(ITM(iw_full_g, mbar_wait(&full[s], rp)))
+#ifdef SPLIT_FULL
             RINGWAIT(ITM(iw_peer_g, mbar_wait(&full_peer[s], rp)))
+#endif
             umma_tf32_lh(tmem_base, outs_lo, hi_k, ring_lo + s * STG, hi_k, idesc_k, 0u);
             if (X3) umma_tf32_lh(tmem_base, outs_lo, hi_k, ring_lo + s * STG + 4096 / 16, hi_k, idesc_k, 1u);   // lo image of W_last
             umma_commit(&empty[s]);
@@ -680,7 +701,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
               TRS(2710)
               RINGWAIT(ITM(iw_full, mbar_wait(&full[s], rp)))
               TRS(2720)
+#ifdef SPLIT_FULL
               RINGWAIT(ITM(iw_peer, mbar_wait(&full_peer[s], rp)))
+#endif
               TRS(2700)
               // stage = [Zbar piece 8 KB | a piece 8 KB]; the accumulator is the TRANSPOSED weight gradient a^T Zbar (A operand =
               // the a piece, M = input features; B operand = the Zbar piece, N = output features), so that a TMEM lane is one
