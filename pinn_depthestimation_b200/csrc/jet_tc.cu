@@ -309,6 +309,20 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr, uint32_t lb
 __device__ __forceinline__ void st_global_v4(float* p, float a, float b, float c, float d) {
   asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// L2 eviction-priority hints for the spill streams
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void st_global_v4_hint(float* p, float a, float b, float c, float d, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "l"(pol) : "memory");
+}
 __device__ __forceinline__ float4 ld_global_v4(const float* p) {
   float4 v;
   asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
@@ -605,8 +619,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         ++jobs;
         tc_fence_after();
       };
+      // all four slices: every warp signals its slices in order, so the last slice's barrier completing means the other three
+      // have completed too -- one poll instead of four (a poll costs hundreds of cycles while the drain's REDs fill the LSU queue)
       auto wait_ready = [&]() {
+#ifdef WAIT_ALL_SLICES
         for (int q = 0; q < 4; ++q) wait_slice();
+#else
+        jobs += 3;
+        wait_slice();
+#endif
       };
       int nedge = 0;
       // D[256 x 256] = OP (K-major, 256 features; 128 rows in each CTA) * weight half-images (K-major, 128 columns in each CTA)
@@ -845,6 +866,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 #ifndef KO_SPILL
 #pragma unroll
       for (int j = 0; j < 4; ++j) st_global_v4(img + img_off(j, b), v[j][0], v[j][1], v[j][2], v[j][3]);
+#endif
+    };
+    // Zbar spill: the two buffers are rewritten every other layer and read once in between -- keep them in L2 (evict_last)
+    // so that the activation images streaming through the cache do not push them out to HBM
+#ifndef NO_ZBAR_HINT
+    const uint64_t pol_z = l2_policy_evict_last();
+#endif
+    auto st_zimg_block = [&](float* img, int b, const float (&v)[4][4]) {
+#ifndef KO_SPILL
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#ifndef NO_ZBAR_HINT
+        st_global_v4_hint(img + img_off(j, b), v[j][0], v[j][1], v[j][2], v[j][3], pol_z);
+#else
+        st_global_v4(img + img_off(j, b), v[j][0], v[j][1], v[j][2], v[j][3]);
+#endif
+      }
 #endif
     };
     auto ld_img_block = [&](const float* img, int b, float (&v)[4][4]) {
@@ -1186,7 +1224,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           else adjoint(ab, act);
           st_op_block(b, ab);
           signal_slice();                   // (the adjoint job of layer L-2 starts once all four slices are in)
-          st_img_block(zdst, b, ab);
+          st_zimg_block(zdst, b, ab);
           if (X3) db_block_x3(dbl, b, zb0);
           else db_block(dbl, b, ab[0]);
         }
@@ -1259,7 +1297,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             st_op_block(b, ab);
             if (hidden) {
               signal_slice();               // (the adjoint job of layer l-1 starts once all four slices are in)
-              st_img_block(zdst, b, ab);
+              st_zimg_block(zdst, b, ab);
               if (X3) db_block_x3(dbl, b, zb0);
               else db_block(dbl, b, ab[0]);
             }
