@@ -151,7 +151,14 @@ __global__ void __launch_bounds__(NT)
   uint64_t* full = reinterpret_cast<uint64_t*>(red + PINN_NSUMS);
 
   const int tid = threadIdx.x;
+#ifndef FP32_CG_FAST
+  // point group fastest: a quarter-warp's 128-bit stores of the activation write-back (row stride 4 * MP = 16 mod 32 banks
+  // between column groups) then cover 32 distinct banks -- with the column group fastest they were 4-way conflicted -- and a
+  // weight fetch is one 128-byte wavefront per warp (8 column groups, broadcast over the point groups) instead of four
+  const int pg = tid % PG, cg = tid / PG;
+#else
   const int cg = tid % CG, pg = tid / CG;
+#endif
   const int L = D.n_linear;
   const int d = D.widths[0], o = D.widths[L];
   const int KP0 = pad4(d), NPo = pad4(o);
