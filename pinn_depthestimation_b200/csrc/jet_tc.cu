@@ -994,6 +994,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       if (!(lane & 4)) atomicAdd(dbl + 64 * b + 16 * half + 4 * cq + 2 * (b4 ? 1 : 0) + (b3 ? 1 : 0), k);
     };
 
+    // Edge-layer gradients (dW0 columns 0..3, db0, dW_last rows 0..3) of this thread's feature, accumulated over ALL tiles of
+    // the CTA in registers and flushed once at kernel exit: per tile they were ~9 scalar atomics per thread onto 2,300
+    // addresses shared by all 148 CTAs -- same-address REDs that kept the LSU queue full into the next tile's layer 0
+    float e0[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, eL[4] = {0.f, 0.f, 0.f, 0.f};
     for (int it = 0; it < my_tiles; ++it) {
       TR_SET(tid == 0)
       TR(1900)
@@ -1190,7 +1194,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           acc[6] = fmaf(z1.z, a, acc[6]), acc[7] = fmaf(z1.w, a, acc[7]);
         }
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
+        for (int c = 0; c < 4; ++c) eL[c] += acc[c];
+#pragma unroll
+        for (int c = 4; c < 8; ++c)
           if (c < o) atomicAdd(A.grad + poffL + (long long)c * TC_H + f, acc[c]);
         if (tid < o) {
           float s = 0.f;
@@ -1348,15 +1354,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             if (c == D.dir_cols[jj]) acc[c] += tj[jj];
         }
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
+        for (int c = 0; c < 4; ++c) e0[c] += acc[c];
+        e0[4] += sb;
+#pragma unroll
+        for (int c = 4; c < 8; ++c)
           if (c < d) atomicAdd(A.grad + (long long)f * d + c, acc[c]);
-        atomicAdd(A.grad + (long long)d * TC_H + f, sb);
       }
       worker_bar();
       TR(1990)
       TCT(12)
     }
     if (BWD) {
+      {
+        const int f = tid & (TC_H - 1);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < d) atomicAdd(A.grad + (long long)f * d + c, e0[c]);
+          if (c < o) atomicAdd(A.grad + poffL + (long long)c * TC_H + f, eL[c]);
+        }
+        atomicAdd(A.grad + (long long)d * TC_H + f, e0[4]);
+      }
       // bias gradients of the hidden layers, accumulated over all tiles of this CTA
       worker_bar();
       for (int i = tid; i < TC_MAX_HH * TC_H; i += TC_WORKERS) {
