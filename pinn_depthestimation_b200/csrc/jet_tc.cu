@@ -531,8 +531,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         mbar_wait(&empty[lane], pph);
         mbar_expect_tx(&full[lane], bytes);
         if (src2) {
+#ifdef KO_DW1COPY
+          tma_load_1d(stage, src, TC_STAGE_BYTES, &full[lane]);   // timing experiment: one 16 KB copy per weight-gradient stage
+#else
           tma_load_1d(stage, src, TC_STAGE_BYTES / 2, &full[lane]);
           tma_load_1d(stage + TC_STAGE_BYTES / 2, src2, TC_STAGE_BYTES / 2, &full[lane]);
+#endif
         } else {
           tma_load_1d(stage, src, bytes, &full[lane]);
         }
