@@ -1135,6 +1135,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       }
       tc_fence_before();
       worker_bar();
+      TR(1211)
       TCT(13)
       // ---------------- residual / misfit epilogue: warp 0, one lane per point ----------------
       if (warp == 0) {
@@ -1147,11 +1148,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
                              EpiArgs{A.targets, nullptr, {nullptr, nullptr, nullptr}, A.out,
                                      {A.dout[0], A.dout[1], A.dout[2]}, A.inv_n_res, A.inv_n_fid, inv_cnt},
                              ls);
+        TR(1212)
 #pragma unroll
         for (int i = 0; i < PINN_NSUMS; ++i) {
           const float v = warp_sum_tc(ls[i]);
           if (lane == 0 && v != 0.f) red[i] += (double)v;
         }
+        TR(1213)
         if (X3 && BWD && isp) {   // adjoint seeds -> hi in the jet's hi row, lo in its lo row (A operand of the reverse last-layer MMA)
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
