@@ -11,8 +11,8 @@
 //   tile            32 points x 4 jet rows = 128 rows per CTA
 //   forward  l      D[256 x 256] = A[256 x 256] * W_l^T          A: smem (K-major), B: W half-images via TMA
 //   adjoint  l      D[256 x 256] = Zbar[256 x 256] * W_l         A: smem (K-major), B: W^T half-images via TMA
-//   weight grad l   D[256 x 256] = Zbar^T * A_in, K = the 256 rows of BOTH tiles; CTA r ends up with dW rows
-//                   [128 r, 128 r + 128)           A, B: MN-major (SWIZZLE_128B_BASE32B) spill pieces via TMA
+//   weight grad l   D[256 x 256] = A_in^T * Zbar (the TRANSPOSED gradient), K = the 256 rows of BOTH tiles; CTA r ends up with
+//                   dW columns [128 r, 128 r + 128) as TMEM lanes   A, B: MN-major (SWIZZLE_128B_BASE32B) spill pieces via TMA
 //   last layer      forward D[256 x 32] = A * W_last^T (N = 32, zero-padded); reverse Abar = seeds * W_last as
 //                   ONE K = 8 MMA whose A operand is the K-major output / seed image
 //   accumulators live in TMEM (512 columns), read back with tcgen05.ld for the tanh / jet / adjoint
@@ -27,24 +27,24 @@
 // features: the tanh' coupling between the value and the tangent rows is thread-local (no shuffles) and
 // tanh is evaluated once per (point, feature).
 //
-// Warp roles (576 threads, one CTA per SM, persistent over tile pairs):
-//   warps 0-15 workers: layer 0, epilogues (TMEM -> registers -> operand image in smem / spill), drains (RED)
-//   warp  16   producer: 1-D TMA bulk copies of weight half-images and spill pieces into a 5-stage ring
+// Warp roles (640 threads, one CTA per SM, persistent over tile pairs):
+//   warps 0-15 workers: layer 0, epilogues (TMEM -> registers -> operand image in smem / spill), drains (RED); 104 registers
+//   warp  16   producer: one lane per ring stage issues the 1-D TMA bulk copies of weight half-images and spill pieces
 //   warp  17   leader: one thread issues every tcgen05.mma / tcgen05.commit of the pair; follower: one lane per
 //              ring stage relays "my stage has landed" to the leader; owns the TMEM allocation
+//   warps 18-19 spare (setmaxnreg moves registers between whole warpgroups: the control warpgroup 16-19 runs on 64)
 //
 // Operand image in shared memory (K-major, no swizzle): element (row m, feature f) at byte
 //   (f/4)*OP_LBO + m*16 + (f%4)*4, OP_LBO = 128*16 + 32: the canonical K-major UMMA layout with
 //   LBO = OP_LBO, SBO = 128; the 32-byte pad makes the 16-byte jets-in-thread accesses conflict-free.
-// Spill image in global memory (G_l, 256 KB per hidden layer l per tile) = the two operands of the weight-gradient
-//   job of layer l, Zbar_l (written in the reverse sweep) and a_{l-1} (written in the forward sweep), in 16-row chunks
-//   of 32 KB: [feature half 0: Zbar 8 KB | a 8 KB][feature half 1: Zbar 8 KB | a 8 KB], each 8 KB piece =
-//   [4 panels of 32 features][16 rows][128 B] with the 32-byte units of a row XOR-swizzled by (row % 4): exactly the
-//   MN-major SWIZZLE_128B_BASE32B shared-memory layout (LBO 2048 between panels, SBO 512 between 4-row atoms), the
-//   only MN-major layout kind::tf32 accepts (tools/umma_mn_probe.cu).  It is row-major per panel, so the epilogue
-//   threads write it straight from registers in full 32-byte sectors and read a_{l-1} back the same way in the
-//   reverse sweep; one CTA of the pair needs exactly one contiguous 16 KB piece per 16 rows (one TMA copy per ring
-//   stage) -- no transposition pass anywhere.
+// Spill images in global memory (128 KB each, per CTA: a_0 .. a_{L-3}, then two Zbar buffers used alternately): the two
+//   operands of the weight-gradient job of layer l are Zbar_l (written in the reverse sweep) and a_{l-1} (written in the
+//   forward sweep).  An image = [16-row chunk (8)][feature half (2)][8 KB piece]; a piece = [4 panels of 32 features][16 rows]
+//   [128 B] with the 32-byte units of a row XOR-swizzled by (row % 4): exactly the MN-major SWIZZLE_128B_BASE32B shared-memory
+//   layout (LBO 2048 between panels, SBO 512 between 4-row atoms), the only MN-major layout kind::tf32 accepts
+//   (tools/umma_mn_probe.cu).  It is row-major per panel, so the epilogue threads write it straight from registers in full
+//   32-byte sectors and read a_{l-1} back the same way in the reverse sweep; a ring stage of the weight-gradient job = the
+//   Zbar piece and the a piece `rank` of one 16-row chunk (two 8 KB copies on one barrier) -- no transposition pass anywhere.
 //
 // Split-operand mode (X3 = true, PINN_PREC_TF32X3): FP32-grade results on the same tensor pipe.  Every operand x is
 // carried as x = hi + lo with hi = tf32(x), lo = tf32(x - hi) (22 mantissa bits together).  A tile holds 16 points;
@@ -108,7 +108,7 @@ struct TcArgs {
   double* sums;
   float* out;
   float* dout[PINN_MAX_DIRS];
-  float* slab;            // per CTA: (L-2) weight-gradient operand images G_l = {Zbar_l, a_{l-1}}
+  float* slab;            // per CTA: L-2 activation images a_0 .. a_{L-3}, then two alternating Zbar buffers
   long long slab_stride;  // floats per CTA
   long long n_points;
   int n_tiles;
