@@ -16,7 +16,7 @@ X = (torch.rand(n, 4, generator=g) * 2 - 1).to(dev)
 T = (0.05 * torch.randn(n, 4, generator=g)).to(dev)
 p = torch.from_numpy(jo.make_params(layers, 1234)).to(dev)
 spec = PassSpec(layers=layers, kind="Navier_Stokes", dirs={"t": 0, "x": 1, "y": 2}, fields={"h": 0, "z": 1, "u": 2, "v": 3},
-                target_cols=[0, 1, 2, 3], precision="tf32")
+                target_cols=[0, 1, 2, 3], precision=(sys.argv[3] if len(sys.argv) > 3 else "tf32"))
 jl = JetLoss(spec, X, T)
 g0 = torch.empty_like(p)
 parts0 = jl.loss_and_grad(p, g0).clone()
