@@ -452,7 +452,9 @@ def main():
                     "frac": achieved / peak,
                     "traffic": tr["dram_bytes_per_point"] * (hi - lo) if tr else None,
                     "traffic_source": tr_src, "peak_source": peak_src, "kernel": info["kernel"],
-                    "kernel_ms": kern_ms, "flops_per_point": F, "points_per_launch": hi - lo,
+                    "kernel_ms": kern_ms, "flops_per_point": F,
+                    "points_per_launch": (hi - lo) // max(1, len(jl._shards(jl.res))),
+                    "jet_launches_per_evaluation": len(jl._shards(jl.res)),
                     "hbm_gbs_streaming": (hi - lo) * (w["layers"][0] + len(w["target_cols"])) * 4
                     / (kern_ms * 1e-3) / 1e9}
         if precision == "tf32x3":
@@ -466,7 +468,8 @@ def main():
                  "loss_parts": [float(v) for v in parts[:3]],
                  "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": "points/s", "ms_per_step": e2e_ms,
                          "h2d_bytes_per_step": (Xh.numel() + Th.numel() + P) * 4, "d2h_bytes_per_step": (P + 4) * 4},
-                 "gpu_launches": 3 * steps, "roofline": roofline, "clocks": clk, "tolerance": info["tolerance"]}
+                 "gpu_launches": jl.launches_per_eval * steps, "roofline": roofline, "clocks": clk,
+                 "tolerance": info["tolerance"]}
         return block, jl, grad
 
     head, jl, grad = measure_mode(args.precision, args.steps, args.warmup, True)
@@ -647,7 +650,9 @@ def main():
             "loss_parts": head["loss_parts"],
             "e2e": head["e2e"],
             "gpu_launches": head["gpu_launches"],
-            "gpu_launches_note": "per step: pack kernel, jet kernel, finalize_kernel (+2 memsets, "
+            "gpu_launches_note": "per step: pack kernel, jet kernel (one per slice of at most fused.SHARD_POINTS points: the "
+                                 "FP32 kernel's 16.8M points run as 8 launches so that no FP32 running sum sees more than "
+                                 "2M points' tiles), finalize_kernel (+2 memsets, "
                                  "+1 NCCL all-reduce when n_gpus>1)",
             "roofline": head["roofline"], "clocks": head["clocks"],
             "tolerance": head["tolerance"],

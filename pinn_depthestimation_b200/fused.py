@@ -94,12 +94,16 @@ class _Pass:
             self._count_mask()
 
     def args(self, params, grad, n_res_global, n_fid_global, flags, out=None, douts=None,
-             seed_out=None, seed_douts=None):
+             seed_out=None, seed_douts=None, shard=None):
+        """shard = (first point, count): evaluate only that slice of the point set (sums and gradient add up over
+        slices because they are sums with the GLOBAL divisors)."""
         a = _cabi.EvalArgs()
         a.params = params.data_ptr()
-        a.inputs = self.inputs.data_ptr() if self.n else None
-        a.targets = self.targets.data_ptr() if self.targets is not None and self.n else None
-        a.n_points = self.n
+        lo, cnt = shard if shard is not None else (0, self.n)
+        a.inputs = self.inputs.data_ptr() + 4 * lo * self.inputs.shape[1] if self.n else None
+        a.targets = (self.targets.data_ptr() + 4 * lo * self.targets.shape[1]
+                     if self.targets is not None and self.n else None)
+        a.n_points = cnt
         a.n_res_global = n_res_global
         a.n_fid_global = n_fid_global
         a.mask_count = self.mask_count.data_ptr() if self.mask_count is not None else None
@@ -118,9 +122,19 @@ class _Pass:
         return a
 
 
+# Points per launch above which a loss+gradient evaluation is split into several launches whose gradients are added
+# outside the kernel: inside one launch a gradient element is the FP32 sum (atomics) of one contribution per tile, and
+# the rounding of ~10^6 such additions shows (tools/accum_noise.py: 2.1e-4 norm-wise for the FP32 kernel's 16-point
+# tiles at 16.8M points, 1.8e-5 for the tensor-core kernel's 64- / 32-point tile pairs, which contract in TMEM first).
+SHARD_POINTS = {"fp32": 1 << 21, "tf32": 1 << 24, "tf32x3": 1 << 24}
+
+
 class JetLoss:
     def __init__(self, spec: PassSpec, inputs: torch.Tensor, targets: Optional[torch.Tensor] = None,
-                 fid: Optional[Tuple[PassSpec, torch.Tensor, torch.Tensor]] = None, group=None):
+                 fid: Optional[Tuple[PassSpec, torch.Tensor, torch.Tensor]] = None, group=None,
+                 shard_points: Optional[int] = None):
+        self.shard_points = int(shard_points) if shard_points else SHARD_POINTS.get(spec.precision, 1 << 21)
+        self._shard_tmp = None
         self.res = _Pass(spec, inputs, targets)
         self.fid = _Pass(*fid) if fid is not None else None
         if self.fid is not None and self.fid.spec.layers != spec.layers:
@@ -145,7 +159,42 @@ class JetLoss:
                                      device=self.device)
 
     # ------------------------------------------------------------------
+    def _shards(self, p: _Pass):
+        k = (p.n + self.shard_points - 1) // self.shard_points
+        m = (p.n + k - 1) // k if k > 0 else 0
+        return [(i * m, min(m, p.n - i * m)) for i in range(k) if p.n - i * m > 0]
+
+    @property
+    def launches_per_eval(self) -> int:
+        """kernel launches of this library per loss+gradient evaluation (pack + jet kernel per pass and shard, finalize)"""
+        passes = [q for q in (self.fid, self.res) if q is not None]
+        if not any(q.n > self.shard_points for q in passes):
+            return 2 * len(passes) + 1
+        return sum(1 + len(self._shards(q)) for q in passes) + 1
+
+    def _launch_sharded(self, params, grad):
+        """loss+gradient in slices of at most `shard_points` points: every slice accumulates into a zeroed scratch vector
+        that is then added to `grad`, so no FP32 running sum sees more than one slice's tiles."""
+        lib = _cabi.lib()
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        if self._shard_tmp is None or self._shard_tmp.numel() != grad.numel():
+            self._shard_tmp = torch.empty_like(grad)
+        tmp = self._shard_tmp
+        grad.zero_()
+        with torch.cuda.device(self.device):
+            for p in [q for q in (self.fid, self.res) if q is not None]:
+                p.sums.zero_()
+                for i, sh in enumerate(self._shards(p)):
+                    tmp.zero_()
+                    flags = _cabi.FLAG_ACCUMULATE | (_cabi.FLAG_SKIP_PACK if i > 0 else 0)
+                    a = p.args(params, tmp, self.n_res_global, self.n_fid_global, flags, shard=sh)
+                    _cabi.check(lib.pinn_jet_loss_fwdbwd(C.byref(p.desc), C.byref(a), st), "sharded pass")
+                    grad.add_(tmp)
+
     def _launch(self, params, grad, want_grad, out=None, douts=None):
+        if want_grad and out is None and douts is None and (
+                self.res.n > self.shard_points or (self.fid is not None and self.fid.n > self.shard_points)):
+            return self._launch_sharded(params, grad)
         lib = _cabi.lib()
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         fn = lib.pinn_jet_loss_fwdbwd if want_grad else lib.pinn_jet_loss_fwd
