@@ -1320,9 +1320,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           for (int u = 0; u < 16; ++u)
             red_add_f32(gcol + (long long)(cb * 16 + u) * TC_H, X3 ? v[u] * A.comp_dw : v[u]);
         }
+#ifdef ZBAR_DISCARD
+        // (-DZBAR_DISCARD, off by default: DRAM writes -16 %, 68 -> 58.5 KB per point in the TF32 mode, but the barrier it
+        // needs costs 0.3 .. 1.8 % of the evaluation time and HBM is not what bounds the kernel: profiles/r2d_zbar_discard.log)
+        // Zbar_l is dead: every MMA of the pair's weight-gradient job has completed (mma_done_b), so both CTAs' copies of
+        // this CTA's buffer have landed.  Drop its lines from L2 without a write-back (the buffer is rewritten in full two
+        // layers on): 1,024 lines of 128 bytes, two per worker thread
+        {
+          const float* zb = zbuf(l);
+#pragma unroll
+          for (int q = 0; q < TC_IMG * 4 / 128 / TC_WORKERS; ++q)
+            asm volatile("discard.global.L2 [%0], 128;" ::"l"(zb + (size_t)(q * TC_WORKERS + tid) * 32) : "memory");
+        }
+#endif
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster_relaxed(rb_free_leader);   // (a releasing arrive would wait for the REDs)
+#ifdef ZBAR_DISCARD
+        worker_bar();   // no warp may start rewriting this buffer (next layer's epilogue) before every discard is out
+#endif
       };
       // the stored activations a_{l-1} the adjoint epilogue of layer l needs are fetched one layer ahead, BEFORE the drain of
       // the previous layer: behind the drain's REDs the loads would sit in the LSU queue until the REDs are through
