@@ -434,6 +434,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   uint64_t* mma_done_b = zt_ready + 2;   // weight-gradient accumulator (TMEM columns 256..511) complete
   uint64_t* rb_free = mma_done_b + 1;    // ... and drained by the workers
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(rb_free + 1);
+  float* w0s = reinterpret_cast<float*>(tmem_ptr + 4);            // [H][4]: columns 0..3 of W0, resident for the whole kernel
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -490,6 +491,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   }
   if (tid < PINN_NSUMS) red[tid] = 0.0;
   for (int i = tid; i < TC_MAX_HH * TC_H; i += TC_THREADS) db_s[i] = 0.f;
+  for (int i = tid; i < TC_H * 4; i += TC_THREADS) w0s[i] = __ldg(w0p + (i >> 2) * 8 + (i & 3));
   if (warp == TC_WORKERS / 32 + 1) {
     tmem_alloc(tmem_ptr, 512);
     tmem_relinquish();
@@ -1072,8 +1074,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int f = 64 * b + 16 * half + 4 * cq + i;
-            const float4 wa = __ldg(reinterpret_cast<const float4*>(w0p + f * 8));
-            const float4 wb = __ldg(reinterpret_cast<const float4*>(w0p + f * 8 + 4));
+            // columns 0..3 of W0 from shared memory (the 28 KB of L1 beside it do not keep the packed copy across a tile);
+            // wider inputs fetch the rest from the packed copy
+            const float4 wa = *reinterpret_cast<const float4*>(w0s + f * 4);
+            const float4 wb = d > 4 ? __ldg(reinterpret_cast<const float4*>(w0p + f * 8 + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
             const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
             float acc = __ldg(b0 + f);
 #pragma unroll
@@ -1552,7 +1556,8 @@ __global__ void pack_tc_kernel(const __grid_constant__ pinn_desc_t D, const floa
 // --------------------------------------------------------------------------------------- host side
 constexpr size_t tc_smem_bytes() {
   return (size_t)OP_BYTES + (size_t)TC_STAGES * TC_STAGE_BYTES +
-         (size_t)TC_M * 8 * 4 + (size_t)TC_TP * 8 * 4 + (size_t)TC_MAX_HH * TC_H * 4 + PINN_NSUMS * 8 + (3 * TC_STAGES + 11) * 8 + 16;
+         (size_t)TC_M * 8 * 4 + (size_t)TC_TP * 8 * 4 + (size_t)TC_MAX_HH * TC_H * 4 + PINN_NSUMS * 8 + (3 * TC_STAGES + 11) * 8 + 16 +
+         (size_t)TC_H * 4 * 4;
 }
 
 // Can this description run on the tensor-core kernel?  (otherwise the caller reports UNSUPPORTED)
