@@ -43,7 +43,7 @@ using namespace pinn;
 
 extern "C" {
 
-const char* pinn_version(void) { return "pinn_b200 0.2 (sm_100a; jet_tc r2d, jet_fp32 r2a)"; }
+const char* pinn_version(void) { return "pinn_b200 0.2 (sm_100a; jet_tc r2e, jet_fp32 r2a)"; }
 const char* pinn_last_error(void) { return g_err; }
 
 int pinn_param_count(const pinn_desc_t* desc, int64_t* n_params) {

@@ -720,7 +720,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       for (int it = 0; it < my_tiles; ++it) {
         TR_SET(true)
         for (int hl = 0; hl < NHH; ++hl) {
-          ITM(i_gemm, gemm_k((uint32_t)(((hl + 1) & 1) * 256), true))   // forward job of layer hl+1, accumulator (hl+1) & 1
+          // forward job of layer hl+1 into TMEM half hl & 1: layer 1 into columns 0..255, because columns 256..511 may still
+          // hold the previous tile's last weight-gradient accumulator (its drain comes after this tile's layer 0)
+          if (BWD && hl == 1 && nB > 0) {
+            ITM(iw_rb, mbar_wait(rb_free, (uint32_t)((nB - 1) & 1)))
+            tc_fence_after();
+          }
+          ITM(i_gemm, gemm_k((uint32_t)((hl & 1) * 256), true))
         }
         {
           // last layer forward: D[256 x 32] = OP * Wlast^T (columns >= o are zero), one ring stage per image
@@ -1051,19 +1057,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     // the CTA in registers and flushed once at kernel exit: per tile they were ~9 scalar atomics per thread onto 2,300
     // addresses shared by all 148 CTAs -- same-address REDs that kept the LSU queue full into the next tile's layer 0
     float e0[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, eL[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int it = 0; it < my_tiles; ++it) {
-      TR_SET(tid == 0)
-      TR(1900)
-      const long long tile = 2ll * (pair + (long long)it * n_pairs) + rank;   // may lie past the end: an all-padding tile
-      const long long p0 = tile * TP;
+    // input tile + layer 0 (d -> 256) on the FP32 pipes -> operand image, slice by slice
+    auto layer0 = [&](int itn) {
+      const long long tile_n = 2ll * (pair + (long long)itn * n_pairs) + rank;   // may lie past the end: an all-padding tile
+      const long long p0n = tile_n * TP;
       for (int i = tid; i < TP * 8; i += TC_WORKERS) {
         const int pq = i >> 3, c = i & 7;
-        const long long gp = p0 + pq;
+        const long long gp = p0n + pq;
         xin[i] = (c < d && gp < A.n_points) ? A.inputs[gp * d + c] : 0.f;
       }
       worker_bar();
-      TCT(0)
-      // ---------------- layer 0 (d -> 256) on the FP32 pipes ----------------
       {
         float x[8];
 #pragma unroll
@@ -1110,6 +1113,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           }
           signal_slice();
         }
+      }
+    };
+    // Tile boundary: the NEXT tile's layer 0 is computed at the end of a tile -- after the layer-0 gradients, before the
+    // drain of layer 1 -- so the first forward job of the next tile is ready when the last weight-gradient job leaves the
+    // tensor pipe; otherwise the pipe idles through drain + layer-0 gradients + input fetch + layer 0 (~16k cycles per pair).
+    bool l0_ready = false;
+    for (int it = 0; it < my_tiles; ++it) {
+      TR_SET(tid == 0)
+      TR(1900)
+      const long long tile = 2ll * (pair + (long long)it * n_pairs) + rank;   // may lie past the end: an all-padding tile
+      const long long p0 = tile * TP;
+      if (!l0_ready) layer0(it);
+      l0_ready = false;
+      TCT(0)
+      {
         // the spill of a_0 is re-read from the operand image AFTER the last slice has been handed over: its stores stall
         // on the LSU queue, and the tensor core should already be running layer 1 while they drain
         if (BWD && NHH >= 1) {
@@ -1139,7 +1157,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
         for (int b = 0; b < TC_NBLK; ++b) {
           float z[4][4];
-          ld_block(b, z, (uint32_t)(l & 1));   // forward accumulators alternate between the two TMEM halves
+          ld_block(b, z, (uint32_t)((l & 1) ^ 1));   // forward accumulators alternate between the two TMEM halves (layer 1: columns 0..255)
           if (X3) {
             activate_x3(z, bl[b]);
           } else {
@@ -1394,7 +1412,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           for (int b = 0; b < TC_NBLK; ++b) ld_img_block(slab + (size_t)(l - 2) * TC_IMG, b, act[b]);   // a_{l-2}, for the next layer
         }
 #endif
-        drain(l);
+        if (l > 1) drain(l);   // (layer 1: after the next tile's layer 0, see below)
         TR(1800 + l)
         TCT(7)
       }
@@ -1435,6 +1453,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           if (c < d) atomicAdd(A.grad + (long long)f * d + c, acc[c]);
       }
       worker_bar();
+      if (it + 1 < my_tiles) {   // the next tile's input and layer 0: its first forward job can follow the last weight-gradient job
+        layer0(it + 1);
+        l0_ready = true;
+      }
+      drain(1);
       TR(1990)
       TCT(12)
     }
